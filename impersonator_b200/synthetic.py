@@ -1,0 +1,167 @@
+"""Synthetic stand-ins for the assets the reference downloads.
+
+Nothing the hot path needs at run time ships with the reference (``assets/pretrains/*`` and
+``outputs/checkpoints/*`` are external downloads, README.md:48-68), so tests, ``bench.py`` and
+``smoke()`` drive the path with:
+
+* a UV-sphere with 84 rings x 82 segments + 2 poles: V = 6890, F = 13776 = 2V - 4, exactly the
+  SMPL counts (utils/nmr.py:620, networks/batch_smpl.py:252), consistently wound so that the
+  reference's back-face test (rasterize_cuda_kernel.cu:57) keeps the camera-facing half;
+* per-frame "poses" = rigid rotations + a smooth vertex displacement, weak-perspective cams
+  ``[s, tx, ty]`` as HMR emits them (utils/nmr.py:10-28);
+* lookup tables shaped like utils/mesh.py:368-421 (``map_fn`` (F+1) x 3 with background row
+  ``[0, 0, 1]``, front/back masks (F+1) x 1);
+* deterministic, key-addressed random weights with the reference's ``state_dict`` keys and
+  shapes (N(0, 0.02) convs as networks/networks.py:54-65, non-trivial norm affines).
+
+Everything is seeded and device independent (generated on CPU with torch.Generator).
+"""
+import hashlib
+import math
+
+import numpy as np
+import torch
+
+SMPL_V = 6890
+SMPL_F = 13776
+
+
+def uv_sphere(rings=84, segments=82, radii=(0.35, 0.9, 0.25)):
+    """-> (verts f32[V,3], faces i32[F,3]) with V = rings*segments + 2, F = 2*rings*segments.
+
+    Winding is chosen so that, after the renderer's y-flip and z-offset (utils/nmr.py:271-273),
+    triangles on the camera side (z < 0 before the offset, i.e. nearer the eye at z = -2.73)
+    pass ``(y2-y0)*(x1-x0) >= (y1-y0)*(x2-x0)``.
+    """
+    verts = []
+    for r in range(rings):
+        theta = math.pi * (r + 1) / (rings + 1)
+        for s in range(segments):
+            phi = 2 * math.pi * s / segments
+            verts.append((math.sin(theta) * math.cos(phi), math.cos(theta), math.sin(theta) * math.sin(phi)))
+    north = len(verts)
+    verts.append((0.0, 1.0, 0.0))
+    south = len(verts)
+    verts.append((0.0, -1.0, 0.0))
+    faces = []
+    for s in range(segments):
+        s1 = (s + 1) % segments
+        faces.append((north, s1, s))
+        base = (rings - 1) * segments
+        faces.append((south, base + s, base + s1))
+    for r in range(rings - 1):
+        for s in range(segments):
+            s1 = (s + 1) % segments
+            a, b = r * segments + s, r * segments + s1
+            c, d = (r + 1) * segments + s, (r + 1) * segments + s1
+            faces.append((a, b, c))
+            faces.append((b, d, c))
+    verts = np.asarray(verts, np.float32) * np.asarray(radii, np.float32)[None]
+    faces = np.asarray(faces, np.int32)
+    return torch.from_numpy(verts), torch.from_numpy(faces)
+
+
+def _rot(ax, ang):
+    c, s = math.cos(ang), math.sin(ang)
+    if ax == 'y':
+        return torch.tensor([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=torch.float32)
+    return torch.tensor([[1, 0, 0], [0, c, -s], [0, s, c]], dtype=torch.float32)
+
+
+def synthetic_frames(batch, seed=1234, base_verts=None):
+    """-> cam f32[B,3], verts f32[B,V,3]: rotation about y ~U(-pi,pi), about x ~U(-0.3,0.3),
+    smooth displacement, cam = [s~U(0.8,1.1), tx,ty~U(-0.1,0.1)]."""
+    g = torch.Generator().manual_seed(seed)
+    if base_verts is None:
+        base_verts, _ = uv_sphere()
+    out_v, out_c = [], []
+    for _ in range(batch):
+        u = torch.rand(8, generator=g)
+        ry = (u[0].item() * 2 - 1) * math.pi
+        rx = (u[1].item() * 2 - 1) * 0.3
+        v = base_verts @ _rot('y', ry).T @ _rot('x', rx).T
+        k = 2 + 3 * u[2].item()
+        amp = 0.02 + 0.02 * u[3].item()
+        v = v + amp * torch.stack([torch.sin(k * v[:, 1] + u[4] * 6), torch.cos(k * v[:, 0] + u[5] * 6),
+                                   torch.sin(k * v[:, 0] * 0.5)], dim=1)
+        out_v.append(v.float())
+        out_c.append(torch.tensor([0.8 + 0.3 * u[6].item(), (u[7].item() * 2 - 1) * 0.1,
+                                   (torch.rand(1, generator=g).item() * 2 - 1) * 0.1], dtype=torch.float32))
+    return torch.stack(out_c), torch.stack(out_v)
+
+
+def synthetic_tables(num_faces=SMPL_F, seed=7):
+    """-> dict(map_fn f32[F+1,3], front_map_fn f32[F+1,1], back_map_fn f32[F+1,1])
+    shaped like utils/mesh.py:368-421 ('uv_seg' :399-402; background row :418-419)."""
+    g = torch.Generator().manual_seed(seed)
+    map_fn = torch.zeros(num_faces + 1, 3)
+    map_fn[:num_faces, :2] = torch.rand(num_faces, 2, generator=g)
+    map_fn[num_faces] = torch.tensor([0.0, 0.0, 1.0])
+    front = (torch.rand(num_faces + 1, 1, generator=g) < 0.05).float()
+    back = (torch.rand(num_faces + 1, 1, generator=g) < 0.05).float()
+    front[num_faces] = 0
+    back[num_faces] = 0
+    return dict(map_fn=map_fn, front_map_fn=front, back_map_fn=back)
+
+
+def _key_gen(seed, key):
+    h = hashlib.sha256(("%d/%s" % (seed, key)).encode()).digest()
+    return torch.Generator().manual_seed(int.from_bytes(h[:7], 'little'))
+
+
+def fill_state_dict(template, seed=0, conv_std=0.02):
+    """Deterministic weights for a ``state_dict``-shaped template (key -> tensor or shape).
+
+    Values depend only on (seed, key, shape): >=2-D tensors ~ N(0, conv_std); 1-D ``*.weight``
+    ~ 1 + 0.1 N(0,1) (norm scales); 1-D ``*.bias`` ~ 0.1 N(0,1); ``running_var`` ~ U(0.5, 1.5);
+    ``running_mean`` ~ 0.1 N(0,1); integer buffers (``num_batches_tracked``) = 0.
+    """
+    out = {}
+    for key, t in template.items():
+        shape = tuple(t.shape) if hasattr(t, 'shape') else tuple(t)
+        dtype = t.dtype if hasattr(t, 'dtype') else torch.float32
+        g = _key_gen(seed, key)
+        if not dtype.is_floating_point:
+            out[key] = torch.zeros(shape, dtype=dtype)
+        elif len(shape) >= 2:
+            out[key] = torch.randn(shape, generator=g) * conv_std
+        elif key.endswith('running_var'):
+            out[key] = 0.5 + torch.rand(shape, generator=g)
+        elif key.endswith('running_mean'):
+            out[key] = 0.1 * torch.randn(shape, generator=g)
+        elif key.endswith('gamma'):
+            out[key] = 0.5 + 0.0 * torch.randn(shape, generator=g)
+        elif key.endswith('weight'):
+            out[key] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            out[key] = 0.1 * torch.randn(shape, generator=g)
+    return out
+
+
+def synthetic_source(image_size=256, seed=99):
+    """-> src_img f32[1,3,H,W] in [-1,1] (smooth, so bilinear warps are well conditioned)."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(1, 3, image_size // 8, image_size // 8, generator=g) * 2 - 1
+    img = torch.nn.functional.interpolate(low, size=(image_size, image_size), mode='bilinear', align_corners=False)
+    return (img + 0.1 * (torch.rand(1, 3, image_size, image_size, generator=g) - 0.5)).clamp(-1, 1)
+
+
+def synthetic_flow(batch, image_size=256, seed=5):
+    """-> T f32[B,H,W,2]: smooth flow in about [-1.1, 1.1] inside an ellipse, -2 outside
+    (the background value cal_bc_transform writes, utils/nmr.py:627)."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(batch, 2, 6, 6, generator=g) * 2.2 - 1.1
+    T = torch.nn.functional.interpolate(low, size=(image_size, image_size), mode='bicubic', align_corners=True)
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, image_size), torch.linspace(-1, 1, image_size), indexing='ij')
+    inside = ((xs / 0.55) ** 2 + (ys / 0.9) ** 2) < 1
+    T = T.permute(0, 2, 3, 1).contiguous()
+    T[:, ~inside] = -2.0
+    return T
+
+
+def synthetic_generator_inputs(batch, image_size=256, seed=11):
+    """-> dict(bg f32[1,4,H,W], src f32[1,6,H,W], tsf f32[B,6,H,W], T f32[B,H,W,2]) in [-1,1]."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=g) * 2 - 1
+    return dict(bg=r(1, 4, image_size, image_size), src=r(1, 6, image_size, image_size),
+                tsf=r(batch, 6, image_size, image_size), T=synthetic_flow(batch, image_size, seed + 1))

@@ -1,0 +1,73 @@
+"""Generates tests/golden/generator.npz -- run ONLY in the build container (needs /root/reference).
+
+Imports the reference's own networks/generator.py (pure torch.nn; ipdb/h5py stubbed), loads the
+deterministic weights of impersonator_b200.synthetic.fill_state_dict(seed=0) into it, runs
+  ImpersonatorGenerator.forward      (networks/generator.py:204-211)   B=1   (BASELINE config 1)
+  encode_src + inference             (:213-214, :277-301)              B=2
+on impersonator_b200.synthetic.synthetic_generator_inputs and stores strided slices of every output.
+It also checks oracle/generator_ref.py (the functional restatement) against the reference modules
+on the full tensors, so the restatement is pinned to the reference here, and the slices pin both
+on the GPU box (where /root/reference does not exist).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+for m in ("ipdb", "h5py"):
+    sys.modules.setdefault(m, types.ModuleType(m))
+sys.path.insert(0, "/root/reference")
+
+from networks.generator import ImpersonatorGenerator          # noqa: E402  (the reference)
+from impersonator_b200 import synthetic                       # noqa: E402
+from oracle import generator_ref as G                         # noqa: E402
+
+
+def sl(t):
+    return t[:, :, 3::8, 5::8].contiguous().numpy()
+
+
+def main():
+    torch.set_grad_enabled(False)
+    net = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6).eval()
+    sd = synthetic.fill_state_dict(net.state_dict(), seed=0)
+    net.load_state_dict(sd, strict=True)
+    keys = sorted(sd.keys())
+    out = {"keys": np.array(keys), "shapes": np.array([str(tuple(sd[k].shape)) for k in keys])}
+
+    inp = synthetic.synthetic_generator_inputs(1, 256, seed=11)
+    ref = net(inp["bg"], inp["src"], inp["tsf"], inp["T"])
+    mine = G.forward(inp["bg"], inp["src"], inp["tsf"], inp["T"], sd)
+    for name, a, b in zip(("img_bg", "src_img", "src_mask", "tsf_img", "tsf_mask"), ref, mine):
+        d = (a - b).abs().max().item()
+        print("forward  %-9s restatement-vs-reference max-abs %.3g" % (name, d))
+        assert d < 1e-5
+        out["fwd_" + name] = sl(a)
+
+    inp2 = synthetic.synthetic_generator_inputs(2, 256, seed=21)
+    enc, res = net.encode_src(inp2["src"])
+    enc2 = [e.expand(2, -1, -1, -1) for e in enc]
+    res2 = [e.expand(2, -1, -1, -1) for e in res]
+    img, mask = net.inference(enc2, res2, inp2["tsf"], inp2["T"])
+    e_m, r_m = G.encode_src(inp2["src"], sd)
+    img_m, mask_m = G.inference(e_m, r_m, inp2["tsf"], inp2["T"], sd)
+    for name, a, b in (("tsf_img", img, img_m), ("tsf_mask", mask, mask_m), ("enc3", enc[3], e_m[3]),
+                       ("res5", res[5], r_m[5])):
+        d = (a - b).abs().max().item()
+        print("inference %-9s restatement-vs-reference max-abs %.3g" % (name, d))
+        assert d < 1e-5
+    out["inf_tsf_img"] = sl(img)
+    out["inf_tsf_mask"] = sl(mask)
+    out["inf_enc3"] = enc[3][:, ::16, ::4, ::4].contiguous().numpy()
+    out["inf_res5"] = res[5][:, ::16, ::4, ::4].contiguous().numpy()
+    np.savez_compressed(os.path.join(HERE, "generator.npz"), **out)
+    print("wrote generator.npz", {k: v.shape for k, v in out.items() if k not in ("keys", "shapes")})
+
+
+if __name__ == "__main__":
+    main()
