@@ -1,0 +1,608 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Replaces the cuDNN calls behind nn.Conv2d / nn.ConvTranspose2d (all bias=False) of
+//   networks/generator.py:8-20 (ResidualBlock 3x3), :80-95 (7x7 stem, 3x3 stride-2 encoders),
+//   :107-124 (ConvTranspose 3x3 s2 p1 op1 decoders, 3x3 "skippers" on cat[skip, d]).
+//
+// GEMM view (no im2col buffer is ever materialised):
+//   D[m, n] = sum_{tap, c} A_tap[m, c] * W[tap][n][c]
+//   m = one output pixel of a 16 x 8 spatial tile (M = 128 = one UMMA),  n = output channel,
+//   A_tap = the same NHWC fp16 activation tensor fetched by TMA at the tap's spatial offset
+//           (out-of-bounds rows/cols are zero-filled by the TMA unit = the conv padding),
+//   W     = weights repacked once to [tap][Cout][Cin] fp16 (K-major rows of 128 bytes).
+// Both operands land in shared memory in the canonical K-major SWIZZLE_128B layout, so each
+// K = 64 stage is 4 x tcgen05.mma (M128 x N_TILE x K16) issued by ONE thread; accumulators
+// live in TMEM (double buffered: the epilogue of tile i overlaps the main loop of tile i+1).
+//
+// Precision: x ~= x_hi + x_lo, w ~= w_hi + w_lo in fp16; with SPLIT the accumulator receives
+// x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (fp32 accumulate), which reproduces the fp32 reference
+// convolution to ~1e-5 (single pass fp16 cannot meet the 1e-3 parity bar).
+//
+// Variants, all through the same kernel:
+//   stride 2      : four parity views of the input (plain strided tensor maps), tap -> view
+//   transposed    : four sub-pixel output phases, each a 1/2/2/4-tap stride-1 conv
+//   concat input  : K chunks 0..chunks0-1 from tensor 0, the rest from tensor 1 (torch.cat free)
+//   7x7 stem      : "row-K" trick -- with 8 channels per pixel, 8 consecutive pixels of a padded
+//                   NHWC8 row are 64 contiguous fp16, so one K = 64 stage covers a whole filter
+//                   row (overlapping-stride tensor map); 7 stages instead of 49.
+// Epilogue: TMEM -> registers -> fp32 NHWC global (128 B per thread) + per-(n, c) sum / sum of
+// squares for the InstanceNorm that follows every conv (warp butterfly -> smem -> one f64 atomic
+// per column per tile).
+#include <cuda.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_H = 16, TILE_W = 8;          // output pixels per tile (M = 128)
+constexpr int KCHUNK = 64;                       // fp16 elements per K stage (128 B swizzle span)
+constexpr int A_BYTES = 128 * 128;
+constexpr int MAX_TAPS = 49;
+constexpr int NUM_THREADS = 192;                 // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+struct ConvParams {
+    CUtensorMap a_hi[4];
+    CUtensorMap a_lo[4];
+    CUtensorMap w_hi;
+    CUtensorMap w_lo;
+    int n_img, tiles_y, tiles_x, n_tiles_n;
+    int dom_h, dom_w;                 // extent of the tile domain (output grid, or phase grid)
+    int ntaps, chunks0, chunks1;
+    signed char dy[MAX_TAPS], dx[MAX_TAPS], tmap[MAX_TAPS];
+    short wtap[MAX_TAPS];
+    float* out; int out_h, out_w, cout;
+    int oy_mul, oy_add, ox_mul, ox_add;
+    double* stats;
+};
+
+template <int N_TILE, bool SPLIT>
+struct Cfg {
+    static constexpr int B_BYTES = N_TILE * 128;
+    static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128
+                                   : (2 * N_TILE <= 256) ? 256 : 512;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int STATS_BYTES = 4 * N_TILE * 2 * 4;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + STATS_BYTES;
+    static_assert(STAGES >= 2, "need at least two pipeline stages");
+    static_assert(2 * N_TILE <= 512, "accumulator double buffer exceeds TMEM");
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("lwb conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// K-major SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(=1)<<16 |
+// SBO(=1024B>>4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Column sums over the 32 lanes of a warp for NV per-lane values: after the butterfly, lane L
+// (L < NV) holds sum over lanes of v[L].  NV = 32: 31 shuffles; NV = 16: 16 + 15 shuffles.
+template <int NV>
+__device__ __forceinline__ float warp_col_sums(float* v, unsigned lane) {
+    if (NV == 16) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+    }
+#pragma unroll
+    for (int off = (NV == 32 ? 16 : 8), cnt = (NV == 32 ? 16 : 8); off >= 1; off >>= 1, cnt >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < cnt; j++) {
+            const float send = up ? v[j] : v[j + cnt];
+            const float keep = up ? v[j + cnt] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// ----------------------------------------------------------------------------------- kernel
+template <int N_TILE, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvParams P)
+{
+    using C = Cfg<N_TILE, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* bar_empty = bar_full + C::STAGES;
+    uint64_t* bar_tfull = bar_empty + C::STAGES;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    float2* s_stats = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);   // [4][N_TILE]
+
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < C::STAGES; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+            for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + b, 1); mbar_init(bar_tempty + b, 4); }
+            fence_barrier_init();
+            fence_proxy_async();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nchunks = P.chunks0 + P.chunks1;
+    const int ksteps = P.ntaps * nchunks;
+    const int m_tiles = P.n_img * P.tiles_y * P.tiles_x;
+    const int total_tiles = m_tiles * P.n_tiles_n;
+
+    if (warp == 0) {
+        // ================================ TMA producer =================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_idx = tile / m_tiles, m_idx = tile % m_tiles;
+                const int img = m_idx / (P.tiles_y * P.tiles_x);
+                const int rem = m_idx % (P.tiles_y * P.tiles_x);
+                const int y0 = (rem / P.tiles_x) * TILE_H, x0 = (rem % P.tiles_x) * TILE_W;
+                for (int s = 0; s < ksteps; s++) {
+                    mbar_wait(bar_empty + stage, phase ^ 1);
+                    uint8_t* st = smem + stage * C::STAGE_BYTES;
+                    mbar_expect_tx(bar_full + stage, (uint32_t)C::STAGE_BYTES);
+                    const int tap = s / nchunks, chunk = s % nchunks;
+                    const bool second = chunk >= P.chunks0;
+                    const int mi = second ? 1 : P.tmap[tap];
+                    const int c0 = (second ? chunk - P.chunks0 : chunk) * KCHUNK;
+                    const int xx = x0 + P.dx[tap], yy = y0 + P.dy[tap];
+                    tma_load_4d(&P.a_hi[mi], st, bar_full + stage, c0, xx, yy, img);
+                    if (SPLIT) tma_load_4d(&P.a_lo[mi], st + A_BYTES, bar_full + stage, c0, xx, yy, img);
+                    uint8_t* sb = st + A_BYTES * (SPLIT ? 2 : 1);
+                    tma_load_3d(&P.w_hi, sb, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE, P.wtap[tap]);
+                    if (SPLIT) tma_load_3d(&P.w_lo, sb + C::B_BYTES, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE, P.wtap[tap]);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ===================================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int abuf = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(bar_tempty + abuf, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * N_TILE);
+                for (int s = 0; s < ksteps; s++) {
+                    mbar_wait(bar_full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + A_BYTES * (SPLIT ? 2 : 1);
+                    const uint32_t b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < KCHUNK / 16; k++) {
+                        const uint64_t da = make_desc(a_hi + k * 32), db = make_desc(b_hi + k * 32);
+                        umma_f16(d_tmem, da, db, idesc, (s > 0 || k > 0) ? 1u : 0u);
+                        if (SPLIT) {
+                            umma_f16(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
+                            umma_f16(d_tmem, make_desc(a_lo + k * 32), db, idesc, 1u);
+                        }
+                    }
+                    umma_commit(bar_empty + stage);                 // smem slot free once these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + abuf);                      // accumulator complete -> epilogue
+                if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue (4 warps) ===========================
+        const int q = warp & 3;                                     // TMEM lane quarter this warp may access
+        const int row = q * 32 + (int)lane;
+        const int ty = row >> 3, tx = row & 7;
+        const int et = threadIdx.x - 64;                            // 0..127
+        int abuf = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_idx = tile / m_tiles, m_idx = tile % m_tiles;
+            const int img = m_idx / (P.tiles_y * P.tiles_x);
+            const int rem = m_idx % (P.tiles_y * P.tiles_x);
+            const int y = (rem / P.tiles_x) * TILE_H + ty, x = (rem % P.tiles_x) * TILE_W + tx;
+            const bool valid = y < P.dom_h && x < P.dom_w;
+            float* optr = P.out + (((size_t)img * P.out_h + (P.oy_mul * y + P.oy_add)) * P.out_w + (P.ox_mul * x + P.ox_add)) * P.cout
+                        + (size_t)n_idx * N_TILE;
+            mbar_wait(bar_tfull + abuf, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * N_TILE);
+            constexpr int CW = N_TILE >= 32 ? 32 : 16;
+#pragma unroll 1
+            for (int c = 0; c < N_TILE / CW; c++) {
+                uint32_t r[CW];
+                if (CW == 32) tmem_ld32(taddr + c * CW, r); else tmem_ld16(taddr + c * CW, r);
+                tmem_ld_wait();
+                if (valid) {
+                    float4* o = reinterpret_cast<float4*>(optr + c * CW);
+#pragma unroll
+                    for (int j = 0; j < CW / 4; j++)
+                        o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                }
+                if (P.stats) {
+                    float v[CW], v2[CW];
+#pragma unroll
+                    for (int j = 0; j < CW; j++) { const float t = valid ? __uint_as_float(r[j]) : 0.f; v[j] = t; v2[j] = t * t; }
+                    const float s1 = warp_col_sums<CW>(v, lane);
+                    const float s2 = warp_col_sums<CW>(v2, lane);
+                    if ((int)lane < CW) s_stats[q * N_TILE + c * CW + lane] = make_float2(s1, s2);
+                }
+            }
+            // all TMEM reads of this buffer are complete: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + abuf);
+            if (P.stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int col = et; col < N_TILE; col += 128) {
+                    const float2 a = s_stats[col], b = s_stats[N_TILE + col], cc = s_stats[2 * N_TILE + col], d = s_stats[3 * N_TILE + col];
+                    double* dst = P.stats + 2 * ((size_t)img * P.cout + (size_t)n_idx * N_TILE + col);
+                    atomicAdd(dst, (double)((a.x + b.x) + (cc.x + d.x)));
+                    atomicAdd(dst + 1, (double)((a.y + b.y) + (cc.y + d.y)));
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// fp16 tensor map, 128B swizzle, zero OOB fill. dims/strides innermost first; strides in bytes for dims 1..rank-1.
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { lwb::set_error("cuTensorMapEncodeTiled entry point not available"); return LWB_E_CUDA; }
+    cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; i++) gstr[i] = strides_bytes[i];
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        lwb::set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] strides [%llu,%llu,%llu] box [%u,%u,%u,%u]",
+                       (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                       (unsigned long long)(rank > 3 ? dims[3] : 0), (unsigned long long)strides_bytes[0],
+                       (unsigned long long)(rank > 2 ? strides_bytes[1] : 0), (unsigned long long)(rank > 3 ? strides_bytes[2] : 0),
+                       box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+        return LWB_E_CUDA;
+    }
+    return LWB_OK;
+}
+
+struct Launch {
+    ConvParams p;
+    int n_tile;
+    bool split;
+    int grid;
+};
+
+template <int N_TILE, bool SPLIT>
+int launch_one(const Launch& L, cudaStream_t st)
+{
+    using C = Cfg<N_TILE, SPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<N_TILE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    k_conv_tc<N_TILE, SPLIT><<<L.grid, NUM_THREADS, C::SMEM_BYTES, st>>>(L.p);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+int launch(const Launch& L, cudaStream_t st)
+{
+    switch (L.n_tile) {
+        case 16:  return L.split ? launch_one<16, true>(L, st) : launch_one<16, false>(L, st);
+        case 64:  return L.split ? launch_one<64, true>(L, st) : launch_one<64, false>(L, st);
+        case 128: return L.split ? launch_one<128, true>(L, st) : launch_one<128, false>(L, st);
+        case 256: return L.split ? launch_one<256, true>(L, st) : launch_one<256, false>(L, st);
+    }
+    lwb::set_error("conv_tc: unsupported N tile %d", L.n_tile);
+    return LWB_E_UNSUPPORTED;
+}
+
+int pick_n_tile(int cout, bool split, int forced)
+{
+    if (forced > 0) return forced;
+    if (cout % 256 == 0 && !split) return 256;
+    if (cout % 128 == 0) return 128;
+    if (cout % 64 == 0) return 64;
+    if (cout % 16 == 0) return 16;
+    return -1;
+}
+
+}  // namespace
+
+struct lwb_conv_plan {
+    int num;
+    Launch launches[4];
+};
+
+// Plain NHWC activation map: dims [C, W, H, N].
+static int map_nhwc(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c)
+{
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
+    const uint32_t box[4] = {KCHUNK, TILE_W, TILE_H, 1};
+    return encode_map(m, base, 4, dims, str, box);
+}
+// Parity view (py, px) of an NHWC tensor for stride-2 convs: element (y', x') = input (2y'+py, 2x'+px).
+static int map_nhwc_parity(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c, int py, int px)
+{
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)((w - px + 1) / 2), (uint64_t)((h - py + 1) / 2), (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)2 * c * 2, (uint64_t)2 * w * c * 2, (uint64_t)h * w * c * 2};
+    const uint32_t box[4] = {KCHUNK, TILE_W, TILE_H, 1};
+    return encode_map(m, base + ((size_t)py * w + px) * c, 4, dims, str, box);
+}
+
+extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
+                                    const uint16_t* x0_hi, const uint16_t* x0_lo,
+                                    const uint16_t* x1_hi, const uint16_t* x1_lo,
+                                    const uint16_t* w_hi, const uint16_t* w_lo,
+                                    float* out_raw, double* stats, lwb_conv_plan** plan_out)
+{
+    LWB_CHECK_ARG(d && x0_hi && w_hi && out_raw && plan_out, "null pointer");
+    const bool split = d->split != 0;
+    LWB_CHECK_ARG(!split || (x0_lo && w_lo), "split mode needs the lo operands");
+    LWB_CHECK_ARG(d->n > 0 && d->h_in > 0 && d->w_in > 0 && d->cout > 0, "non-positive size");
+    LWB_CHECK_ARG(d->cout % 16 == 0, "cout must be a multiple of 16");
+    const int n_tile = pick_n_tile(d->cout, split, d->n_tile);
+    LWB_CHECK_ARG(n_tile > 0 && d->cout % n_tile == 0, "no N tile divides cout");
+
+    lwb_conv_plan* plan = new (std::nothrow) lwb_conv_plan();
+    LWB_CHECK_ARG(plan, "out of host memory");
+    plan->num = 0;
+    int rc = LWB_OK;
+    auto fail = [&](int code) { delete plan; return code; };
+    const int sms = lwb::sm_count();
+
+    auto finish = [&](Launch& L, int dom_h, int dom_w) {
+        ConvParams& p = L.p;
+        p.n_img = d->n;
+        p.dom_h = dom_h; p.dom_w = dom_w;
+        p.tiles_y = lwb::ceil_div(dom_h, TILE_H); p.tiles_x = lwb::ceil_div(dom_w, TILE_W);
+        p.n_tiles_n = d->cout / n_tile;
+        p.out = out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
+        p.stats = stats;
+        L.n_tile = n_tile; L.split = split;
+        const long total = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+        L.grid = (int)(total < sms ? total : sms);
+    };
+
+    if (d->rowk) {
+        // 7x7 stem through the row-K trick.  Input: padded NHWC8 buffer [n, h_in + kh - 1, wp, 8] whose
+        // pixel (y + pad, x + pad) holds input pixel (y, x); wp >= w_in + 8.  One K = 64 stage = 8
+        // consecutive pixels x 8 channels of a padded row = one whole filter row (8th tap weight = 0).
+        LWB_CHECK_ARG(d->stride == 1 && !d->transposed && d->kw <= 8 && d->cin0 == 8 && d->cin1 == 0, "row-K needs stride 1, kw <= 8, 8 channels");
+        LWB_CHECK_ARG(d->h_out == d->h_in && d->w_out == d->w_in && d->row_pitch >= d->w_in + 8, "row-K shape");
+        Launch& L = plan->launches[plan->num++];
+        memset(&L.p, 0, sizeof(L.p));
+        const int hp = d->h_in + d->kh - 1;
+        const uint64_t dims[4] = {64, (uint64_t)d->w_in, (uint64_t)hp, (uint64_t)d->n};
+        const uint64_t str[3] = {16, (uint64_t)d->row_pitch * 16, (uint64_t)hp * d->row_pitch * 16};
+        const uint32_t box[4] = {KCHUNK, TILE_W, TILE_H, 1};
+        if ((rc = encode_map(&L.p.a_hi[0], x0_hi, 4, dims, str, box)) != LWB_OK) return fail(rc);
+        if (split && (rc = encode_map(&L.p.a_lo[0], x0_lo, 4, dims, str, box)) != LWB_OK) return fail(rc);
+        const uint64_t wd[3] = {64, (uint64_t)d->cout, (uint64_t)d->kh};
+        const uint64_t ws[2] = {128, (uint64_t)d->cout * 128};
+        const uint32_t wb[3] = {KCHUNK, (uint32_t)n_tile, 1};
+        if ((rc = encode_map(&L.p.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+        if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+        L.p.ntaps = d->kh; L.p.chunks0 = 1; L.p.chunks1 = 0;
+        for (int ky = 0; ky < d->kh; ky++) { L.p.dy[ky] = (signed char)ky; L.p.dx[ky] = 0; L.p.tmap[ky] = 0; L.p.wtap[ky] = (short)ky; }
+        L.p.oy_mul = 1; L.p.ox_mul = 1; L.p.oy_add = 0; L.p.ox_add = 0;
+        finish(L, d->h_out, d->w_out);
+        *plan_out = plan;
+        return LWB_OK;
+    }
+
+    LWB_CHECK_ARG(d->cin0 % KCHUNK == 0 && d->cin1 % KCHUNK == 0 && d->cin0 > 0, "input channels must be multiples of 64");
+    LWB_CHECK_ARG(d->cin1 == 0 || (x1_hi && (!split || x1_lo)), "second input missing");
+    const int cin_total = d->cin0 + d->cin1;
+    const int ntaps_w = d->kh * d->kw;
+    LWB_CHECK_ARG(ntaps_w <= MAX_TAPS, "too many filter taps");
+    const uint64_t wd[3] = {(uint64_t)cin_total, (uint64_t)d->cout, (uint64_t)ntaps_w};
+    const uint64_t ws[2] = {(uint64_t)cin_total * 2, (uint64_t)d->cout * cin_total * 2};
+    const uint32_t wb[3] = {KCHUNK, (uint32_t)n_tile, 1};
+
+    if (d->transposed) {
+        // ConvTranspose2d(k=3, s=2, p=1, output_padding=1): out[2i+a, 2j+b] gathers, per axis,
+        //   a = 0: (k=1, d=0)            a = 1: (k=2, d=0), (k=0, d=+1)        (oy = 2*iy - 1 + ky)
+        LWB_CHECK_ARG(d->kh == 3 && d->kw == 3 && d->stride == 2 && d->pad == 1 && d->cin1 == 0, "transposed conv: only k3 s2 p1 op1");
+        LWB_CHECK_ARG(d->h_out == 2 * d->h_in && d->w_out == 2 * d->w_in, "transposed conv output must be 2x input");
+        for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) {
+            Launch& L = plan->launches[plan->num++];
+            memset(&L.p, 0, sizeof(L.p));
+            if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0)) != LWB_OK) return fail(rc);
+            if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0)) != LWB_OK) return fail(rc);
+            if ((rc = encode_map(&L.p.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+            if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+            const int ky_list[2][2] = {{1, -1}, {2, 0}}, d_list[2][2] = {{0, 0}, {0, 1}}, cnt[2] = {1, 2};
+            int t = 0;
+            for (int i = 0; i < cnt[a]; i++) for (int j = 0; j < cnt[b]; j++) {
+                L.p.dy[t] = (signed char)d_list[a][i]; L.p.dx[t] = (signed char)d_list[b][j];
+                L.p.tmap[t] = 0; L.p.wtap[t] = (short)(ky_list[a][i] * 3 + ky_list[b][j]);
+                t++;
+            }
+            L.p.ntaps = t; L.p.chunks0 = d->cin0 / KCHUNK; L.p.chunks1 = 0;
+            L.p.oy_mul = 2; L.p.ox_mul = 2; L.p.oy_add = a; L.p.ox_add = b;
+            finish(L, d->h_in, d->w_in);
+        }
+        *plan_out = plan;
+        return LWB_OK;
+    }
+
+    LWB_CHECK_ARG(d->stride == 1 || d->stride == 2, "stride must be 1 or 2");
+    LWB_CHECK_ARG(d->stride == 1 || d->cin1 == 0, "concat input only with stride 1");
+    Launch& L = plan->launches[plan->num++];
+    memset(&L.p, 0, sizeof(L.p));
+    if (d->stride == 1) {
+        if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0)) != LWB_OK) return fail(rc);
+        if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0)) != LWB_OK) return fail(rc);
+        if (d->cin1) {
+            if ((rc = map_nhwc(&L.p.a_hi[1], x1_hi, d->n, d->h_in, d->w_in, d->cin1)) != LWB_OK) return fail(rc);
+            if (split && (rc = map_nhwc(&L.p.a_lo[1], x1_lo, d->n, d->h_in, d->w_in, d->cin1)) != LWB_OK) return fail(rc);
+        }
+    } else {
+        for (int py = 0; py < 2; py++) for (int px = 0; px < 2; px++) {
+            if ((rc = map_nhwc_parity(&L.p.a_hi[py * 2 + px], x0_hi, d->n, d->h_in, d->w_in, d->cin0, py, px)) != LWB_OK) return fail(rc);
+            if (split && (rc = map_nhwc_parity(&L.p.a_lo[py * 2 + px], x0_lo, d->n, d->h_in, d->w_in, d->cin0, py, px)) != LWB_OK) return fail(rc);
+        }
+    }
+    if ((rc = encode_map(&L.p.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+    if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+    int t = 0;
+    for (int ky = 0; ky < d->kh; ky++) for (int kx = 0; kx < d->kw; kx++) {
+        const int oy = ky * d->dil - d->pad, ox = kx * d->dil - d->pad;       // input offset relative to stride*y
+        if (d->stride == 1) {
+            L.p.dy[t] = (signed char)oy; L.p.dx[t] = (signed char)ox; L.p.tmap[t] = 0;
+        } else {
+            // input coordinate 2y + oy = 2(y + floor(oy/2)) + (oy mod 2): parity view + index shift
+            const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
+            L.p.dy[t] = (signed char)((oy - py) / 2); L.p.dx[t] = (signed char)((ox - px) / 2);
+            L.p.tmap[t] = (signed char)(py * 2 + px);
+        }
+        L.p.wtap[t] = (short)t;
+        t++;
+    }
+    L.p.ntaps = t; L.p.chunks0 = d->cin0 / KCHUNK; L.p.chunks1 = d->cin1 / KCHUNK;
+    L.p.oy_mul = 1; L.p.ox_mul = 1; L.p.oy_add = 0; L.p.ox_add = 0;
+    finish(L, d->h_out, d->w_out);
+    *plan_out = plan;
+    return LWB_OK;
+}
+
+extern "C" int lwb_conv_plan_run(const lwb_conv_plan* plan, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(plan, "null plan");
+    for (int i = 0; i < plan->num; i++) {
+        const int rc = launch(plan->launches[i], (cudaStream_t)stream);
+        if (rc != LWB_OK) return rc;
+    }
+    return LWB_OK;
+}
+
+extern "C" void lwb_conv_plan_destroy(lwb_conv_plan* plan) { delete plan; }
+
+extern "C" int lwb_conv_plan_num_launches(const lwb_conv_plan* plan) { return plan ? plan->num : 0; }
+
+extern "C" int lwb_conv2d_nhwc(const lwb_conv_desc* d,
+                               const uint16_t* x0_hi, const uint16_t* x0_lo,
+                               const uint16_t* x1_hi, const uint16_t* x1_lo,
+                               const uint16_t* w_hi, const uint16_t* w_lo,
+                               float* out_raw, double* stats, lwb_stream_t stream)
+{
+    lwb_conv_plan* plan = nullptr;
+    int rc = lwb_conv_plan_create(d, x0_hi, x0_lo, x1_hi, x1_lo, w_hi, w_lo, out_raw, stats, &plan);
+    if (rc != LWB_OK) return rc;
+    rc = lwb_conv_plan_run(plan, stream);
+    lwb_conv_plan_destroy(plan);
+    return rc;
+}

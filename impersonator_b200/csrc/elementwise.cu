@@ -1,0 +1,355 @@
+// HBM-bound glue kernels of the conv engine (sm_100a): layout conversion, weight packing,
+// InstanceNorm + ReLU + residual + Liquid-Warping-Block add, output heads + composite.
+//
+// networks/generator.py:8-20 (ResidualBlock), :80-95 (Conv+IN+ReLU), :283-295 (tsf + warp),
+// :183-184 (tanh / sigmoid heads), models/imitator.py:330-331 (composite).
+#include "common.cuh"
+#include "sample.cuh"
+
+namespace {
+
+using lwb::split_half;
+
+// ---------------------------------------------------------------------------------------------
+// weights: OIHW (Conv2d) / IOHW (ConvTranspose2d) fp32 -> [tap][cout_pad][cin_pad] fp16 hi/lo
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_weight(const float* __restrict__ w, int cout, int cin, int kh, int kw, int transposed,
+                              int cout_pad, int cin_pad, __half* __restrict__ hi, __half* __restrict__ lo)
+{
+    const long total = (long)kh * kw * cout_pad * cin_pad;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin_pad);
+        const int co = (int)((i / cin_pad) % cout_pad);
+        const int tap = (int)(i / ((long)cin_pad * cout_pad));
+        float v = 0.f;
+        if (ci < cin && co < cout) {
+            const int ky = tap / kw, kx = tap % kw;
+            v = transposed ? w[(((size_t)ci * cout + co) * kh + ky) * kw + kx]
+                           : w[(((size_t)co * cin + ci) * kh + ky) * kw + kx];
+        }
+        __half h, l;
+        split_half(v, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
+// First-layer packing for the row-contiguous 7x7 trick (see conv_tc.cu): [ky][cout_pad][kxs*cpx]
+// with K index = kx*cpx + c  (kx < kw real taps, the rest zero).
+__global__ void k_pack_weight_rowk(const float* __restrict__ w, int cout, int cin, int kh, int kw,
+                                   int cout_pad, int cpx, int kxs, __half* __restrict__ hi, __half* __restrict__ lo)
+{
+    const int kk = kxs * cpx;
+    const long total = (long)kh * cout_pad * kk;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % kk);
+        const int co = (int)((i / kk) % cout_pad);
+        const int ky = (int)(i / ((long)kk * cout_pad));
+        const int kx = k / cpx, c = k % cpx;
+        float v = 0.f;
+        if (kx < kw && c < cin && co < cout) v = w[(((size_t)co * cin + c) * kh + ky) * kw + kx];
+        __half h, l;
+        split_half(v, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC fp16 hi/lo into a (possibly spatially padded) buffer [n, hp, wp, c_pad]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc_split(
+        const float* __restrict__ x, int n, int c, int h, int w, int c_pad,
+        int hp, int wp, int oy, int ox, __half* __restrict__ hi, __half* __restrict__ lo)
+{
+    const long total = (long)n * hp * wp;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int px = (int)(i % wp), py = (int)((i / wp) % hp), b = (int)(i / ((long)wp * hp));
+    const int y = py - oy, xx = px - ox;
+    const bool in = y >= 0 && y < h && xx >= 0 && xx < w;
+    const size_t plane = (size_t)h * w;
+    const float* src = x + (size_t)b * c * plane + (in ? (size_t)y * w + xx : 0);
+    for (int ch = 0; ch < c_pad; ch++) {
+        const float v = (in && ch < c) ? __ldg(src + ch * plane) : 0.f;
+        __half a, l;
+        split_half(v, a, l);
+        hi[i * c_pad + ch] = a;
+        if (lo) lo[i * c_pad + ch] = l;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_nhwc_to_nchw(
+        const float* __restrict__ x, int n, int c, int h, int w, int c_stride, float* __restrict__ out)
+{
+    // tile transpose through shared memory: 32 pixels x 32 channels
+    __shared__ float tile[32][33];
+    const long npix = (long)h * w;
+    const int b = blockIdx.z;
+    const long p0 = (long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 256 threads: ty 0..7
+    for (int j = ty; j < 32; j += 8) {
+        const long p = p0 + j;
+        const int ch = c0 + tx;
+        tile[j][tx] = (p < npix && ch < c) ? x[((size_t)b * npix + p) * c_stride + ch] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int ch = c0 + j;
+        const long p = p0 + tx;
+        if (p < npix && ch < c) out[((size_t)b * c + ch) * npix + p] = tile[tx][j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm statistics (sum, sumsq in f64 from the conv epilogue) -> per-(n,c) scale/shift
+//   y = gamma*(x-mean)*rstd + beta = x*scale + shift        (biased variance, eps inside the sqrt)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_finalize_stats(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, int n, int c, double inv_hw,
+                                 float2* __restrict__ ss)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    const int ch = i % c;
+    const double mean = stats[2 * i] * inv_hw;
+    double var = stats[2 * i + 1] * inv_hw - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
+    ss[i] = make_float2(g * rstd, bt - (float)mean * g * rstd);
+}
+
+// Plain (two-pass, fp64) statistics for tensors that did not come out of the conv epilogue.
+__global__ void __launch_bounds__(256) k_stats_nhwc(const float* __restrict__ x, int hw, int c, double* __restrict__ stats)
+{
+    // grid: (c/32 rounded up, n, splits); block 256 = 8 pixel lanes x 32 channels
+    const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int b = blockIdx.y;
+    const int lane_p = threadIdx.x >> 5;
+    double s = 0, q = 0;
+    if (ch < c) {
+        for (long p = (long)blockIdx.z * 8 + lane_p; p < hw; p += (long)gridDim.z * 8) {
+            const float v = x[((size_t)b * hw + p) * c + ch];
+            s += v; q += (double)v * v;
+        }
+    }
+    __shared__ double sh[2][8][32];
+    sh[0][lane_p][threadIdx.x & 31] = s;
+    sh[1][lane_p][threadIdx.x & 31] = q;
+    __syncthreads();
+    if (lane_p == 0 && ch < c) {
+        for (int j = 1; j < 8; j++) { s += sh[0][j][threadIdx.x & 31]; q += sh[1][j][threadIdx.x & 31]; }
+        atomicAdd(stats + 2 * ((size_t)b * c + ch), s);
+        atomicAdd(stats + 2 * ((size_t)b * c + ch) + 1, q);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = act(x*scale + shift) + residual + warp(src, T)  ->  fp32 and/or fp16 hi/lo, NHWC
+// one thread = one pixel x 8 channels (32B fp32 loads, 16B fp16 stores)
+// ---------------------------------------------------------------------------------------------
+struct NormActParams {
+    const float* raw; const float2* ss; int relu;
+    int n, h, w, c;
+    const float* residual;
+    const float* warp_src; int src_batch; const float* T; int th, tw, align_corners;
+    float* y_f32; __half* y_hi; __half* y_lo;
+};
+
+__global__ void __launch_bounds__(256) k_norm_act(NormActParams P)
+{
+    const int groups = P.c >> 3;
+    const long total = (long)P.n * P.h * P.w * groups;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % groups);
+    const long pixg = i / groups;                       // global pixel index (n,h,w)
+    const int hw = P.h * P.w;
+    const int b = (int)(pixg / hw), pix = (int)(pixg % hw);
+    const size_t off = (size_t)pixg * P.c + g * 8;
+
+    float v[8];
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(P.raw + off));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(P.raw + off) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    }
+    if (P.ss) {
+        const float2* ss = P.ss + (size_t)b * P.c + g * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const float2 s = __ldg(ss + k); v[k] = fmaf(v[k], s.x, s.y); }
+    }
+    if (P.relu) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = fmaxf(v[k], 0.f);
+    }
+    if (P.residual) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(P.residual + off));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(P.residual + off) + 1);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += c.x; v[5] += c.y; v[6] += c.z; v[7] += c.w;
+    }
+    if (P.warp_src) {
+        const int y = pix / P.w, x = pix % P.w;
+        float gx, gy;
+        lwb::flow_at(P.T + (size_t)b * P.th * P.tw * 2, P.th, P.tw, P.h, P.w, y, x, gx, gy);
+        lwb::Taps tp;
+        lwb::make_taps(gx, gy, P.h, P.w, P.align_corners, tp);
+        const float* src = P.warp_src + (size_t)(P.src_batch == 1 ? 0 : b) * hw * P.c + g * 8;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int offs[4] = {tp.o00, tp.o00 + 1, tp.o00 + P.w, tp.o00 + P.w + 1};
+        const float wt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if (tp.m & (1 << t)) {
+                const float4* p = reinterpret_cast<const float4*>(src + (size_t)offs[t] * P.c);
+                const float4 a = __ldg(p), c = __ldg(p + 1);
+                acc[0] += a.x * wt[t]; acc[1] += a.y * wt[t]; acc[2] += a.z * wt[t]; acc[3] += a.w * wt[t];
+                acc[4] += c.x * wt[t]; acc[5] += c.y * wt[t]; acc[6] += c.z * wt[t]; acc[7] += c.w * wt[t];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] += acc[k];
+    }
+    if (P.y_f32) {
+        float4* o = reinterpret_cast<float4*>(P.y_f32 + off);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (P.y_hi) {
+        __align__(16) __half hh[8];
+        __align__(16) __half ll[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) split_half(v[k], hh[k], ll[k]);
+        *reinterpret_cast<uint4*>(P.y_hi + off) = *reinterpret_cast<const uint4*>(hh);
+        if (P.y_lo) *reinterpret_cast<uint4*>(P.y_lo + off) = *reinterpret_cast<const uint4*>(ll);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// heads: color = tanh(raw[0:3]), mask = sigmoid(raw[3]), pred = mask*bg + (1-mask)*color
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_heads(const float* __restrict__ raw, int n, int hw, int c_stride,
+                                               const float* __restrict__ bg, int bg_batch,
+                                               float* __restrict__ color, float* __restrict__ mask, float* __restrict__ pred)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n * hw) return;
+    const int b = (int)(i / hw), p = (int)(i % hw);
+    const float4 r = __ldg(reinterpret_cast<const float4*>(raw + (size_t)i * c_stride));
+    const float col[3] = {tanhf(r.x), tanhf(r.y), tanhf(r.z)};
+    const float m = 1.f / (1.f + expf(-r.w));
+    if (mask) mask[i] = m;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (color) color[((size_t)b * 3 + k) * hw + p] = col[k];
+        if (pred && bg) {
+            const float bgv = __ldg(bg + ((size_t)(bg_batch == 1 ? 0 : b) * 3 + k) * hw + p);
+            pred[((size_t)b * 3 + k) * hw + p] = m * bgv + (1.f - m) * col[k];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int lwb_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int transposed,
+                                    int cout_pad, int cin_pad, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(w && w_hi, "null pointer");
+    LWB_CHECK_ARG(cout > 0 && cin > 0 && kh > 0 && kw > 0 && cout_pad >= cout && cin_pad >= cin, "bad sizes");
+    const long total = (long)kh * kw * cout_pad * cin_pad;
+    k_pack_weight<<<(int)min((total + 255) / 256, 4096l), 256, 0, (cudaStream_t)stream>>>(
+        w, cout, cin, kh, kw, transposed, cout_pad, cin_pad, (__half*)w_hi, (__half*)w_lo);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+extern "C" int lwb_pack_conv_weight_rowk(const float* w, int cout, int cin, int kh, int kw,
+                                         int cout_pad, int cpx, int kxs, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(w && w_hi, "null pointer");
+    LWB_CHECK_ARG(cout > 0 && cin > 0 && cin <= cpx && kw <= kxs && cout_pad >= cout, "bad sizes");
+    const long total = (long)kh * cout_pad * kxs * cpx;
+    k_pack_weight_rowk<<<(int)min((total + 255) / 256, 4096l), 256, 0, (cudaStream_t)stream>>>(
+        w, cout, cin, kh, kw, cout_pad, cpx, kxs, (__half*)w_hi, (__half*)w_lo);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+extern "C" int lwb_nchw_to_nhwc_split(const float* x, int n, int c, int h, int w, int c_pad,
+                                      int hp, int wp, int oy, int ox,
+                                      uint16_t* hi, uint16_t* lo, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(x && hi, "null pointer");
+    LWB_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && c_pad >= c && hp >= h + oy && wp >= w + ox && oy >= 0 && ox >= 0, "bad sizes");
+    const long total = (long)n * hp * wp;
+    k_nchw_to_nhwc_split<<<lwb::ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, n, c, h, w, c_pad, hp, wp, oy, ox, (__half*)hi, (__half*)lo);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+extern "C" int lwb_nhwc_to_nchw(const float* x, int n, int c, int h, int w, int c_stride, float* out, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(x && out, "null pointer");
+    LWB_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && c_stride >= c && n <= 65535, "bad sizes");
+    dim3 grid(lwb::ceil_div((long)h * w, 32), lwb::ceil_div(c, 32), n);
+    k_nhwc_to_nchw<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, c, h, w, c_stride, out);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+extern "C" int lwb_instance_stats_nhwc(const float* x, int n, int h, int w, int c, double* stats, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(x && stats, "null pointer");
+    LWB_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && n <= 65535, "bad sizes");
+    const int hw = h * w;
+    const int splits = max(1, min(64, hw / 256));
+    dim3 grid(lwb::ceil_div(c, 32), n, splits);
+    k_stats_nhwc<<<grid, 256, 0, (cudaStream_t)stream>>>(x, hw, c, stats);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const float* gamma, const float* beta,
+                                 float eps, int relu, int n, int h, int w, int c,
+                                 const float* residual,
+                                 const float* warp_src, int src_batch, const float* T, int th, int tw, int align_corners,
+                                 float* scale_shift_ws,
+                                 float* y_f32, uint16_t* y_hi, uint16_t* y_lo, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(raw, "null pointer");
+    LWB_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0, "channels must be a multiple of 8");
+    LWB_CHECK_ARG(!stats || scale_shift_ws, "stats needs the scale/shift workspace [n,c,2] f32");
+    LWB_CHECK_ARG(!warp_src || (T && th > 0 && tw > 0 && (src_batch == 1 || src_batch == n)), "bad warp arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stats) {
+        k_finalize_stats<<<lwb::ceil_div((long)n * c, 256), 256, 0, st>>>(
+            stats, gamma, beta, eps, n, c, 1.0 / ((double)h * w), (float2*)scale_shift_ws);
+        LWB_LAUNCH_OK();
+    }
+    NormActParams P;
+    P.raw = raw; P.ss = stats ? (const float2*)scale_shift_ws : nullptr; P.relu = relu;
+    P.n = n; P.h = h; P.w = w; P.c = c;
+    P.residual = residual;
+    P.warp_src = warp_src; P.src_batch = src_batch; P.T = T; P.th = th; P.tw = tw; P.align_corners = align_corners;
+    P.y_f32 = y_f32; P.y_hi = (__half*)y_hi; P.y_lo = (__half*)y_lo;
+    const long total = (long)n * h * w * (c / 8);
+    k_norm_act<<<lwb::ceil_div(total, 256), 256, 0, st>>>(P);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+extern "C" int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride,
+                                   const float* bg, int bg_batch,
+                                   float* color, float* mask, float* pred, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(raw, "null pointer");
+    LWB_CHECK_ARG(n > 0 && h > 0 && w > 0 && c_stride >= 4 && (c_stride % 4) == 0, "bad sizes");
+    LWB_CHECK_ARG(!bg || bg_batch == 1 || bg_batch == n, "bg_batch must be 1 or n");
+    k_heads<<<lwb::ceil_div((long)n * h * w, 256), 256, 0, (cudaStream_t)stream>>>(
+        raw, n, h * w, c_stride, bg, bg_batch, color, mask, pred);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}

@@ -1,0 +1,255 @@
+"""Tensor-level front-ends of the C ABI (one function per entry point of include/lwb_b200.h).
+
+Each function checks devices/dtypes/contiguity, allocates outputs with torch (device memory is
+torch's job), and calls the library on torch's current stream.  No arithmetic happens here.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, LwbError, check, lib, ptr, stream, _chk_cuda
+
+# utils/nmr.py:177: eye = [0, 0, -(1/tan(30 deg) + 1)], cast to float32 by look_at.py:33
+EYE_Z = float(np.float32(-(1. / np.tan(np.radians(30)) + 1)))
+NEAR, FAR = 0.1, 100.0              # rasterize.py:10-11 defaults (what render_fim_wim really uses)
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, "raster")
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def raster_forward_face_index_map(faces, face_index_map, weight_map, depth_map, image_size,
+                                  near=NEAR, far=FAR, faces_inv=None, flip_rows=False):
+    """rasterize_cuda.forward_face_index_map (rasterize_cuda.cpp:70-95): in-place on pre-filled maps."""
+    _chk_cuda(faces, face_index_map, weight_map, depth_map, faces_inv)
+    if faces.dtype != torch.float32 or face_index_map.dtype != torch.int32 or weight_map.dtype != torch.float32:
+        raise LwbError("faces/weight_map must be float32 and face_index_map int32")
+    B, F = faces.shape[:2]
+    ws = _workspace(lib().lwb_raster_workspace_bytes(B, image_size), faces.device)
+    check(lib().lwb_raster_forward_face_index_map(
+        ptr(faces), B, F, image_size, near, far, ptr(face_index_map), ptr(weight_map), ptr(depth_map),
+        ptr(faces_inv), 1 if flip_rows else 0, ptr(ws), stream()), "lwb_raster_forward_face_index_map")
+    return face_index_map, weight_map, depth_map
+
+
+def correspond(cam, verts, face_idx, image_size, map_fn, src_p2verts, src_img=None, align_corners=False,
+               want_f2verts=False, near=NEAR, far=FAR, out=None):
+    """Fused render_fim_wim + encode_fim + cal_bc_transform + image warp + concat (lwb_correspond).
+
+    -> dict(fim i32[B,H,W], wim f32[B,H,W,3], T f32[B,H,W,2], tsf_inputs f32[B,3+C,H,W],
+            tsf_img / cond = channel views of tsf_inputs, f2verts f32[B,F,3,3] | None)
+    """
+    _chk_cuda(cam, verts, face_idx, map_fn, src_p2verts, src_img)
+    B, V = verts.shape[:2]
+    F = face_idx.shape[0]
+    C = map_fn.shape[1]
+    if face_idx.dtype != torch.int32:
+        raise LwbError("face_idx must be int32")
+    if map_fn.shape[0] != F + 1:
+        raise LwbError("map_fn must have F+1 rows (background last)")
+    sb = src_p2verts.shape[0]
+    dev = verts.device
+    s = image_size
+    if out is None:
+        out = dict(fim=torch.empty((B, s, s), dtype=torch.int32, device=dev),
+                   wim=torch.empty((B, s, s, 3), dtype=torch.float32, device=dev),
+                   T=torch.empty((B, s, s, 2), dtype=torch.float32, device=dev),
+                   tsf_inputs=torch.empty((B, 3 + C, s, s), dtype=torch.float32, device=dev),
+                   f2verts=torch.empty((B, F, 3, 3), dtype=torch.float32, device=dev) if want_f2verts else None)
+    ws = _workspace(lib().lwb_raster_workspace_bytes(B, s), dev)
+    check(lib().lwb_correspond(
+        ptr(cam), ptr(verts), ptr(face_idx), B, V, F, s, near, far, EYE_Z,
+        ptr(map_fn), C, ptr(src_p2verts), ptr(src_img), sb, 1 if align_corners else 0,
+        ptr(out["fim"]), ptr(out["wim"]), ptr(out["T"]), ptr(out["tsf_inputs"]), ptr(out.get("f2verts")),
+        ptr(ws), stream()), "lwb_correspond")
+    out["tsf_img"] = out["tsf_inputs"][:, :3]
+    out["cond"] = out["tsf_inputs"][:, 3:]
+    return out
+
+
+def warp_nchw(x, T, align_corners=False, out=None, accumulate=False):
+    """transform / stn (networks/generator.py:303-320): x [Bs,C,h,w], T [B,TH,TW,2] -> [B,C,h,w]."""
+    _chk_cuda(x, T, out)
+    if x.dtype != torch.float32 or T.dtype != torch.float32:
+        raise LwbError("warp expects float32")
+    sb, C, h, w = x.shape
+    B, th, tw = T.shape[:3]
+    if out is None:
+        out = torch.empty((B, C, h, w), dtype=torch.float32, device=x.device)
+    check(lib().lwb_warp_nchw(ptr(x), sb, C, h, w, ptr(T), B, th, tw, 1 if align_corners else 0,
+                              ptr(out), 1 if accumulate else 0, stream()), "lwb_warp_nchw")
+    return out
+
+
+def pack_conv_weight(w, transposed=False, cout_pad=None, cin_pad=None, split=True):
+    """OIHW / IOHW fp32 -> ([tap][cout_pad][cin_pad] fp16 hi, lo)."""
+    _chk_cuda(w)
+    w = w.float().contiguous()
+    if transposed:
+        cin, cout, kh, kw = w.shape
+    else:
+        cout, cin, kh, kw = w.shape
+    cout_pad = cout_pad or cout
+    cin_pad = cin_pad or cin
+    hi = torch.empty((kh * kw, cout_pad, cin_pad), dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi) if split else None
+    check(lib().lwb_pack_conv_weight(ptr(w), cout, cin, kh, kw, 1 if transposed else 0, cout_pad, cin_pad,
+                                     ptr(hi), ptr(lo), stream()), "lwb_pack_conv_weight")
+    return hi, lo
+
+
+def pack_conv_weight_rowk(w, cout_pad=None, cpx=8, kxs=8, split=True):
+    """7x7 stem weights -> [ky][cout_pad][kxs*cpx] fp16 hi, lo (K index = kx*cpx + c)."""
+    _chk_cuda(w)
+    w = w.float().contiguous()
+    cout, cin, kh, kw = w.shape
+    cout_pad = cout_pad or cout
+    hi = torch.empty((kh, cout_pad, kxs * cpx), dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi) if split else None
+    check(lib().lwb_pack_conv_weight_rowk(ptr(w), cout, cin, kh, kw, cout_pad, cpx, kxs, ptr(hi), ptr(lo), stream()),
+          "lwb_pack_conv_weight_rowk")
+    return hi, lo
+
+
+def nchw_to_nhwc_split(x, c_pad=None, pad_hw=(0, 0, 0, 0), hi=None, lo=None, split=True):
+    """NCHW fp32 -> NHWC fp16 hi/lo [n, h+top+bottom, w+left+right, c_pad]; pad_hw = (top, bottom, left, right)."""
+    _chk_cuda(x, hi, lo)
+    n, c, h, w = x.shape
+    c_pad = c_pad or c
+    top, bottom, left, right = pad_hw
+    hp, wp = h + top + bottom, w + left + right
+    if hi is None:
+        hi = torch.empty((n, hp, wp, c_pad), dtype=torch.float16, device=x.device)
+        lo = torch.empty_like(hi) if split else None
+    check(lib().lwb_nchw_to_nhwc_split(ptr(x), n, c, h, w, c_pad, hp, wp, top, left, ptr(hi), ptr(lo), stream()),
+          "lwb_nchw_to_nhwc_split")
+    return hi, lo
+
+
+def nhwc_to_nchw(x, c=None, out=None):
+    _chk_cuda(x, out)
+    n, h, w, cs = x.shape
+    c = c or cs
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(lib().lwb_nhwc_to_nchw(ptr(x), n, c, h, w, cs, ptr(out), stream()), "lwb_nhwc_to_nchw")
+    return out
+
+
+class ConvPlan(object):
+    """One conv layer bound to fixed buffers (lwb_conv_plan): build once, run every step."""
+
+    def __init__(self, desc, x0, x1, w, out_raw, stats):
+        """x0 / x1 / w: (hi, lo) tensor pairs (x1 may be None); out_raw fp32 NHWC; stats f64 [n,cout,2] or None."""
+        self._keep = (x0, x1, w, out_raw, stats)
+        self.desc = desc
+        handle = ctypes.c_void_p()
+        x1 = x1 or (None, None)
+        check(lib().lwb_conv_plan_create(ctypes.byref(desc), ptr(x0[0]), ptr(x0[1]), ptr(x1[0]), ptr(x1[1]),
+                                         ptr(w[0]), ptr(w[1]), ptr(out_raw), ptr(stats), ctypes.byref(handle)),
+              "lwb_conv_plan_create")
+        self._h = handle
+        self.num_launches = lib().lwb_conv_plan_num_launches(handle)
+
+    def run(self):
+        check(lib().lwb_conv_plan_run(self._h, stream()), "lwb_conv_plan_run")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().lwb_conv_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def make_conv_desc(n, h_in, w_in, cin0, cout, kh, kw, stride=1, pad=0, dil=1, cin1=0, transposed=False,
+                   split=True, rowk=False, row_pitch=0, n_tile=0):
+    if transposed:
+        h_out, w_out = 2 * h_in, 2 * w_in
+    elif rowk:
+        h_out, w_out = h_in, w_in
+    else:
+        h_out = (h_in + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        w_out = (w_in + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    return ConvDesc(n=n, h_in=h_in, w_in=w_in, h_out=h_out, w_out=w_out, cin0=cin0, cin1=cin1, cout=cout,
+                    kh=kh, kw=kw, stride=stride, pad=pad, dil=dil, transposed=1 if transposed else 0,
+                    split=1 if split else 0, rowk=1 if rowk else 0, row_pitch=row_pitch, n_tile=n_tile)
+
+
+def instance_stats_nhwc(x, stats=None):
+    _chk_cuda(x, stats)
+    n, h, w, c = x.shape
+    if stats is None:
+        stats = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    check(lib().lwb_instance_stats_nhwc(ptr(x), n, h, w, c, ptr(stats), stream()), "lwb_instance_stats_nhwc")
+    return stats
+
+
+def norm_act_nhwc(raw, stats, gamma, beta, relu, ws, eps=1e-5, residual=None, warp_src=None, T=None,
+                  align_corners=False, y_f32=None, y_hi=None, y_lo=None):
+    """InstanceNorm + ReLU + residual + LWB warp-add on an NHWC fp32 tensor (lwb_norm_act_nhwc)."""
+    _chk_cuda(raw, stats, gamma, beta, residual, warp_src, T, ws, y_f32, y_hi, y_lo)
+    n, h, w, c = raw.shape
+    sb, th, tw = 0, 0, 0
+    if warp_src is not None:
+        sb = warp_src.shape[0]
+        th, tw = T.shape[1:3]
+    check(lib().lwb_norm_act_nhwc(ptr(raw), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if relu else 0, n, h, w, c,
+                                  ptr(residual), ptr(warp_src), sb, ptr(T), th, tw, 1 if align_corners else 0,
+                                  ptr(ws), ptr(y_f32), ptr(y_hi), ptr(y_lo), stream()), "lwb_norm_act_nhwc")
+
+
+def pack_head_weights(w_img, w_att):
+    _chk_cuda(w_img, w_att)
+    w4 = torch.empty((49, 64, 4), dtype=torch.float32, device=w_img.device)
+    check(lib().lwb_pack_head_weights(ptr(w_img.float().contiguous()), ptr(w_att.float().contiguous()), ptr(w4), stream()),
+          "lwb_pack_head_weights")
+    return w4
+
+
+def conv7x7_heads_nhwc(x, w4, out=None):
+    _chk_cuda(x, w4, out)
+    n, h, w, c = x.shape
+    if c != 64:
+        raise LwbError("heads expect 64 input channels")
+    if out is None:
+        out = torch.empty((n, h, w, 4), dtype=torch.float32, device=x.device)
+    check(lib().lwb_conv7x7_heads_nhwc(ptr(x), ptr(w4), n, h, w, ptr(out), stream()), "lwb_conv7x7_heads_nhwc")
+    return out
+
+
+def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, mask=None, pred=None):
+    _chk_cuda(raw, bg, color, mask, pred)
+    n, h, w, cs = raw.shape
+    dev = raw.device
+    if color is None and want_color:
+        color = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+    if mask is None and want_mask:
+        mask = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+    if pred is None and bg is not None:
+        pred = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+    check(lib().lwb_heads_composite(ptr(raw), n, h, w, cs, ptr(bg), bg.shape[0] if bg is not None else 0,
+                                    ptr(color), ptr(mask), ptr(pred), stream()), "lwb_heads_composite")
+    return color, mask, pred
+
+
+def conv2d_direct_nchw(x, w, bias=None, stride=1, pad=0, dil=1):
+    _chk_cuda(x, w, bias)
+    n, cin, h, wd = x.shape
+    cout, _, kh, kw = w.shape
+    ho = (h + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    wo = (wd + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
+    check(lib().lwb_conv2d_direct_nchw(ptr(x), ptr(w), ptr(bias), n, cin, h, wd, cout, kh, kw, stride, pad, dil,
+                                       ptr(out), stream()), "lwb_conv2d_direct_nchw")
+    return out

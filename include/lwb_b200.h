@@ -1,0 +1,191 @@
+/*
+ * lwb_b200 -- C ABI of the B200-native Liquid-Warping hot path (sm_100a).
+ *
+ * Drop-in boundary for svip-lab/impersonator's per-frame inference path.  Every entry point
+ * takes plain device pointers + sizes and a cudaStream_t (passed as void*), returns 0 on
+ * success or a negative LWB_E_* code (lwb_last_error() gives the text).  No torch types.
+ * All launches are asynchronous on the caller's stream; nothing here synchronises.
+ *
+ * Each declaration cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef LWB_B200_H_
+#define LWB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LWB_OK            0
+#define LWB_E_INVALID    -1   /* bad argument (null pointer, unsupported size) */
+#define LWB_E_CUDA       -2   /* a CUDA runtime/driver call failed */
+#define LWB_E_UNSUPPORTED -3  /* shape outside what the kernels were built for */
+
+typedef void* lwb_stream_t;   /* cudaStream_t */
+
+int         lwb_version(void);
+const char* lwb_last_error(void);
+/* SM count / compute capability of the current device (0 when no device): lets the host fail loudly. */
+int         lwb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Rasterizer.  Replaces the pybind11 entry point
+ *   neural_renderer.cuda.rasterize.forward_face_index_map
+ *   thirdparty/neural_renderer/neural_renderer/cuda/rasterize_cuda.cpp:70-95  (launcher
+ *   rasterize_cuda_kernel.cu:613-668, kernels :40-186), as called from rasterize.py:164-169.
+ * Same contract: the caller allocates and pre-fills face_index_map (-1), weight_map (0),
+ * depth_map (far); only covered pixels are written.  faces_inv (nullable) receives kernel_1's
+ * per-face inverse matrices (caller zero-fills, culled faces are left untouched).
+ * flip_rows = 0 gives the native kernel's row order (row 0 = bottom, +y up); flip_rows = 1 writes
+ * row (H-1-y) instead, i.e. folds the torch.flip of rasterize.py:334-338 into the store.
+ * workspace: lwb_raster_workspace_bytes(batch, image_size) bytes of device scratch (z-buffer).
+ * face_index_map is bit-exact with the reference kernels compiled by the same nvcc.
+ * ------------------------------------------------------------------------------------------ */
+size_t lwb_raster_workspace_bytes(int batch, int image_size);
+int lwb_raster_forward_face_index_map(
+        const float* faces /* [B,F,3,3] */, int batch, int num_faces, int image_size,
+        float near, float far,
+        int32_t* face_index_map /* [B,H,W] */, float* weight_map /* [B,H,W,3] */,
+        float* depth_map /* [B,H,W], nullable */, float* faces_inv /* [B,F,3,3], nullable */,
+        int flip_rows, void* workspace, lwb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused correspondence pass = SMPLRenderer.render_fim_wim + encode_fim + cal_bc_transform +
+ * the image-level warp and concat of Imitator.transfer_params_by_smpl:
+ *   utils/nmr.py:263-278 (proj :10-28, y-flip :271, look_at look_at.py:48-60 with the constant
+ *   eye of utils/nmr.py:177, gather vertices_to_faces.py:17-21), rasterize.py:22-98,334-338,
+ *   utils/nmr.py:328-341, utils/nmr.py:617-659, models/imitator.py:259-260.
+ * Inputs : cam [B,3] = (s,tx,ty); verts [B,V,3]; face_idx [F,3] (shared by the batch);
+ *          map_fn [(F+1), map_c] (row F = background, hit by fim == -1);
+ *          src_p2verts [src_batch,F,3,2] with src_batch in {1,B} (models/imitator.py:105-107);
+ *          src_img [src_batch,3,H,W] (nullable -> no image warp).
+ * Outputs: fim i32 [B,H,W], wim [B,H,W,3] (top row first, i.e. after the flips),
+ *          T [B,H,W,2] (-2 where uncovered), tsf_inputs [B,3+map_c,H,W] = cat[tsf_img, cond]
+ *          (channels 0..2 = grid_sample(src_img, T), 3.. = cond), f2verts [B,F,3,3] (nullable).
+ *          All outputs are fully written (no pre-fill needed).
+ * align_corners selects the grid_sample convention (0 = torch>=1.3 default, the oracle;
+ * 1 = torch 1.2 behaviour the reference was written against).
+ * ------------------------------------------------------------------------------------------ */
+int lwb_correspond(
+        const float* cam, const float* verts, const int32_t* face_idx,
+        int batch, int num_verts, int num_faces, int image_size, float near, float far,
+        float eye_z /* z of the look_at eye, utils/nmr.py:177, as float32 */,
+        const float* map_fn, int map_c,
+        const float* src_p2verts, const float* src_img, int src_batch, int align_corners,
+        int32_t* fim, float* wim, float* T, float* tsf_inputs, float* f2verts,
+        void* workspace, lwb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bilinear warp = ImpersonatorGenerator.transform / stn / resize_trans
+ *   networks/generator.py:303-320 (F.interpolate(T, (h,w), bilinear, align_corners=True) followed
+ *   by F.grid_sample(x, T_scale), zeros padding) and models/imitator.py:259.
+ * x [src_batch,C,h,w] NCHW fp32 (src_batch in {1,B}: one source broadcast over the frame batch,
+ * which torch's grid_sampler cannot do), T [B,TH,TW,2].  When (TH,TW) != (h,w) the flow is
+ * resized on the fly (transform); out [B,C,h,w].  accumulate != 0 adds into out (the "+ warp").
+ * ------------------------------------------------------------------------------------------ */
+int lwb_warp_nchw(const float* x, int src_batch, int channels, int h, int w,
+                  const float* T, int batch, int th, int tw, int align_corners,
+                  float* out, int accumulate, lwb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Conv engine (NHWC, tcgen05 implicit GEMM).  Replaces the cuDNN calls behind nn.Conv2d /
+ * nn.ConvTranspose2d / nn.InstanceNorm2d of networks/generator.py:8-20,77-134,163-184.
+ * Activations are channels-last fp16 pairs (hi + lo, x ~= hi + lo) so that three tensor-core
+ * passes (hi*hi + hi*lo + lo*hi, fp32 accumulate) reproduce fp32 convolution to ~1e-5
+ * (SURVEY.md section 0 fact 4); split = 0 runs the single hi*hi pass ("fast" mode).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Repack an OIHW (Conv2d) or IOHW (ConvTranspose2d, transposed != 0) fp32 weight into the
+ * engine's [tap][Cout_pad][Cin_pad] fp16 hi/lo layout (done once at load time). w_lo nullable. */
+int lwb_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int transposed,
+                         int cout_pad, int cin_pad, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream);
+/* Row-K packing for the 7x7 stem: [ky][cout_pad][kxs*cpx], K index = kx*cpx + c (zero beyond kw / cin). */
+int lwb_pack_conv_weight_rowk(const float* w, int cout, int cin, int kh, int kw,
+                              int cout_pad, int cpx, int kxs, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream);
+
+/* NCHW fp32 -> NHWC fp16 hi/lo [n, hp, wp, c_pad]; input pixel (y,x) lands at (y+oy, x+ox), the rest
+ * (spatial border, channels >= c) is zero.  hp >= h+oy, wp >= w+ox.  lo nullable. */
+int lwb_nchw_to_nhwc_split(const float* x, int n, int c, int h, int w, int c_pad,
+                           int hp, int wp, int oy, int ox,
+                           uint16_t* hi, uint16_t* lo, lwb_stream_t stream);
+/* NHWC fp32 [n,h,w,c_stride] (first c channels) -> NCHW fp32 [n,c,h,w]. */
+int lwb_nhwc_to_nchw(const float* x, int n, int c, int h, int w, int c_stride, float* out, lwb_stream_t stream);
+
+typedef struct lwb_conv_desc {
+    int n, h_in, w_in;        /* input  [n, h_in, w_in, cin]  (NHWC fp16 hi/lo) */
+    int h_out, w_out;         /* output [n, h_out, w_out, cout] (NHWC fp32, raw conv result) */
+    int cin0, cin1;           /* channels of input 0 / input 1 (virtual torch.cat, cin1 = 0 if single); x64 */
+    int cout;                 /* multiple of 16 */
+    int kh, kw, stride, pad, dil;
+    int transposed;           /* ConvTranspose2d(k=3, s=2, p=1, output_padding=1) when != 0 */
+    int split;                /* 1 = 3-pass fp16 split (parity mode), 0 = single pass ("fast") */
+    int rowk;                 /* 1 = 7x7-stem row-K mode: input is a padded NHWC8 buffer (see conv_tc.cu) */
+    int row_pitch;            /* rowk: pixels per padded row (>= w_in + 8) */
+    int n_tile;               /* 0 = auto; else force the N tile (16/64/128/256, must divide cout) */
+} lwb_conv_desc;
+
+/* A plan owns the TMA descriptors of one conv layer bound to fixed device buffers; creating it
+ * costs a few driver calls, running it is one launch (four for a transposed conv).
+ * out_raw = conv(x) (no bias); stats [n, cout, 2] f64 += per-(n,c) (sum, sum of squares) over
+ * H*W (nullable; caller zero-fills) -- the InstanceNorm statistics, fused into the epilogue. */
+typedef struct lwb_conv_plan lwb_conv_plan;
+int  lwb_conv_plan_create(const lwb_conv_desc* d,
+                          const uint16_t* x0_hi, const uint16_t* x0_lo,
+                          const uint16_t* x1_hi, const uint16_t* x1_lo,
+                          const uint16_t* w_hi, const uint16_t* w_lo,
+                          float* out_raw, double* stats, lwb_conv_plan** plan);
+int  lwb_conv_plan_run(const lwb_conv_plan* plan, lwb_stream_t stream);
+int  lwb_conv_plan_num_launches(const lwb_conv_plan* plan);
+void lwb_conv_plan_destroy(lwb_conv_plan* plan);
+/* create + run + destroy */
+int lwb_conv2d_nhwc(const lwb_conv_desc* d,
+                    const uint16_t* x0_hi, const uint16_t* x0_lo,
+                    const uint16_t* x1_hi, const uint16_t* x1_lo,
+                    const uint16_t* w_hi, const uint16_t* w_lo,
+                    float* out_raw, double* stats, lwb_stream_t stream);
+
+/* Per-(n,c) sum / sum-of-squares of an NHWC fp32 tensor into stats [n,c,2] f64 (+=, caller zero-fills):
+ * the InstanceNorm statistics for tensors that did not come out of lwb_conv2d_nhwc. */
+int lwb_instance_stats_nhwc(const float* x, int n, int h, int w, int c, double* stats, lwb_stream_t stream);
+
+/* InstanceNorm2d(affine, eps) [+ ReLU] [+ residual] [+ LWB warp] applied to a raw conv output,
+ * emitting the next layer's operands:  y = act(gamma*(x-mean)*rstd + beta) + res + warp(src, T)
+ *   networks/generator.py:13-20 (ResidualBlock), :80-95 (encoders), :283-295 (the "+ warp" of the LWB).
+ * raw [n,h,w,c] fp32; stats from the conv epilogue (nullable -> no normalisation); gamma/beta [c];
+ * residual (nullable) [n,h,w,c] fp32; warp_src (nullable) [src_batch,h,w,c] fp32 NHWC sampled at
+ * T [n,TH,TW,2] resized to (h,w) (generator.py:303-320).  scale_shift_ws: [n,c,2] f32 scratch.
+ * Outputs (each nullable): y_f32 [n,h,w,c]; y_hi / y_lo fp16 [n,h,w,c].  c % 8 == 0. */
+int lwb_norm_act_nhwc(const float* raw, const double* stats, const float* gamma, const float* beta,
+                      float eps, int relu, int n, int h, int w, int c,
+                      const float* residual,
+                      const float* warp_src, int src_batch, const float* T, int th, int tw, int align_corners,
+                      float* scale_shift_ws,
+                      float* y_f32, uint16_t* y_hi, uint16_t* y_lo, lwb_stream_t stream);
+
+/* 7x7 output heads of the generator (networks/generator.py:126-134): img_reg (64->3) and
+ * attetion_reg (64->1) as ONE 64->4 convolution, x [n,h,w,64] fp32 NHWC, w4 [49][64][4] fp32
+ * (tap-major, output channel innermost: 0..2 = img_reg, 3 = attetion_reg), out [n,h,w,4] fp32. */
+int lwb_pack_head_weights(const float* w_img /* [3,64,7,7] */, const float* w_att /* [1,64,7,7] */,
+                          float* w4, lwb_stream_t stream);
+int lwb_conv7x7_heads_nhwc(const float* x, const float* w4, int n, int h, int w, float* out, lwb_stream_t stream);
+
+/* Output heads + composite:  color = tanh(raw[...,0:3]), mask = sigmoid(raw[...,3]),
+ * pred = mask*bg + (1-mask)*color   (networks/generator.py:183-184, models/imitator.py:330-331).
+ * raw [n,h,w,c_stride] fp32 NHWC (channels 0..3 used); bg [bg_batch,3,h,w] NCHW (nullable -> no pred).
+ * color [n,3,h,w], mask [n,1,h,w], pred [n,3,h,w] NCHW, each nullable. */
+int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride,
+                        const float* bg, int bg_batch,
+                        float* color, float* mask, float* pred, lwb_stream_t stream);
+
+/* Direct (CUDA-core) convolution, NCHW fp32, arbitrary kernel / stride / dilation, optional bias:
+ * the once-per-source inpaintor layers (networks/inpaintor.py:12-47) and odd shapes. */
+int lwb_conv2d_direct_nchw(const float* x, const float* w, const float* bias,
+                           int n, int cin, int h, int wd, int cout, int kh, int kw,
+                           int stride, int pad, int dil, float* out, lwb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWB_B200_H_ */

@@ -1,0 +1,194 @@
+"""GPU parity of the conv engine (tcgen05 implicit GEMM) and its glue kernels against plain
+torch fp32 ops on CPU (the same ATen ops the reference's nn.Conv2d / ConvTranspose2d /
+InstanceNorm2d / grid_sample calls resolve to).  Tolerances: split (parity) mode 2e-4 of the
+output scale; single-pass fp16 ("fast") mode 2e-2."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from impersonator_b200 import kernels as K
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def report(name, got, ref):
+    d = (got - ref).abs()
+    scale = ref.abs().max().item() + 1e-12
+    idx = np.unravel_index(int(d.argmax()), d.shape)
+    print("%s: max-abs %.3e (ref scale %.3e, rel %.3e) at %s; mean-abs %.3e; nonfinite %d"
+          % (name, d.max().item(), scale, d.max().item() / scale, idx, d.mean().item(),
+             int((~torch.isfinite(got)).sum())))
+    return d.max().item() / scale
+
+
+def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x1=None, n_tile=0, stats=True):
+    """x [n,c,h,w] fp32 CPU, w OIHW (or IOHW when transposed) -> NCHW fp32 CPU result, stats."""
+    n, c0, h, wd = x.shape
+    xs = K.nchw_to_nhwc_split(x.to(cuda), split=split)
+    x1s = K.nchw_to_nhwc_split(x1.to(cuda), split=split) if x1 is not None else None
+    ws = K.pack_conv_weight(w.to(cuda), transposed=transposed, split=split)
+    cout = w.shape[1] if transposed else w.shape[0]
+    kh, kw = w.shape[2:]
+    d = K.make_conv_desc(n, h, wd, c0, cout, kh, kw, stride=stride, pad=pad, dil=dil,
+                         cin1=0 if x1 is None else x1.shape[1], transposed=transposed, split=split, n_tile=n_tile)
+    out = torch.full((n, d.h_out, d.w_out, cout), float("nan"), dtype=torch.float32, device=cuda)
+    st = torch.zeros((n, cout, 2), dtype=torch.float64, device=cuda) if stats else None
+    plan = K.ConvPlan(d, xs, x1s, ws, out, st)
+    plan.run()
+    torch.cuda.synchronize()
+    return K.nhwc_to_nchw(out).cpu(), (st.cpu() if stats else None)
+
+
+def check_stats(st, ref):
+    s = ref.double().sum(dim=(2, 3))
+    q = (ref.double() ** 2).sum(dim=(2, 3))
+    e1 = ((st[..., 0] - s).abs().max() / (s.abs().max() + 1e-9)).item()
+    e2 = ((st[..., 1] - q).abs().max() / (q.abs().max() + 1e-9)).item()
+    print("stats rel err: sum %.3e sumsq %.3e" % (e1, e2))
+    assert e1 < 1e-3 and e2 < 1e-3
+
+
+CASES = [
+    # name, n, cin, cout, h, w, k, stride, pad, n_tile
+    ("3x3_64_64_16x8", 1, 64, 64, 16, 8, 3, 1, 1, 0),
+    ("3x3_64_64_32", 2, 64, 64, 32, 32, 3, 1, 1, 0),
+    ("3x3_128_128_32", 2, 128, 128, 32, 32, 3, 1, 1, 0),
+    ("3x3_512_512_32", 2, 512, 512, 32, 32, 3, 1, 1, 0),
+    ("3x3_64_16_n16", 1, 64, 16, 32, 32, 3, 1, 1, 16),
+    ("1x1_64_64", 1, 64, 64, 32, 32, 1, 1, 0, 0),
+    ("3x3_s2_64_128_64", 2, 64, 128, 64, 64, 3, 2, 1, 0),
+    ("3x3_s2_256_512_64", 1, 256, 512, 64, 64, 3, 2, 1, 0),
+    ("3x3_ragged_40x24", 1, 64, 64, 40, 24, 3, 1, 1, 0),
+    ("7x7_64_64", 1, 64, 64, 32, 32, 7, 1, 3, 0),
+]
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv2d(cuda, case, split):
+    name, n, cin, cout, h, w, k, stride, pad, n_tile = case
+    x = rnd(n, cin, h, w, seed=1)
+    wt = rnd(cout, cin, k, k, seed=2, scale=0.05)
+    ref = F.conv2d(x, wt, stride=stride, padding=pad)
+    got, st = run_conv(cuda, x, wt, stride=stride, pad=pad, split=split, n_tile=n_tile)
+    rel = report(name + ("/split" if split else "/fast"), got, ref)
+    assert rel < (2e-4 if split else 2e-2)
+    if split:
+        check_stats(st, ref)
+
+
+@pytest.mark.parametrize("split", [True, False])
+def test_conv_transpose(cuda, split):
+    for cin, cout, h in ((128, 64, 32), (512, 256, 32)):
+        x = rnd(2, cin, h, h, seed=3)
+        wt = rnd(cin, cout, 3, 3, seed=4, scale=0.05)
+        ref = F.conv_transpose2d(x, wt, stride=2, padding=1, output_padding=1)
+        got, st = run_conv(cuda, x, wt, stride=2, pad=1, transposed=True, split=split)
+        rel = report("convT_%d_%d" % (cin, cout), got, ref)
+        assert rel < (2e-4 if split else 2e-2)
+        if split:
+            check_stats(st, ref)
+
+
+@pytest.mark.parametrize("split", [True, False])
+def test_conv_concat_inputs(cuda, split):
+    """skippers: conv(cat[skip, d]) without materialising the cat (networks/generator.py:177-179)."""
+    a, b = rnd(2, 64, 32, 32, seed=5), rnd(2, 128, 32, 32, seed=6)
+    wt = rnd(64, 192, 3, 3, seed=7, scale=0.05)
+    ref = F.conv2d(torch.cat([a, b], dim=1), wt, padding=1)
+    got, _ = run_conv(cuda, a, wt, split=split, x1=b)
+    assert report("concat", got, ref) < (2e-4 if split else 2e-2)
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("size", [32, 256])
+def test_stem_7x7_rowk(cuda, split, size):
+    """7x7 stem (6 -> 64 channels) through the row-K layout (networks/generator.py:80-84)."""
+    n = 2
+    x = rnd(n, 6, size, size, seed=8)
+    wt = rnd(64, 6, 7, 7, seed=9, scale=0.05)
+    ref = F.conv2d(x, wt, padding=3)
+    pitch = size + 8
+    xs = K.nchw_to_nhwc_split(x.to(cuda), c_pad=8, pad_hw=(3, 3, 3, 5), split=split)
+    ws = K.pack_conv_weight_rowk(wt.to(cuda), split=split)
+    d = K.make_conv_desc(n, size, size, 8, 64, 7, 7, stride=1, pad=3, split=split, rowk=True, row_pitch=pitch)
+    out = torch.full((n, size, size, 64), float("nan"), dtype=torch.float32, device=cuda)
+    st = torch.zeros((n, 64, 2), dtype=torch.float64, device=cuda)
+    K.ConvPlan(d, xs, None, ws, out, st).run()
+    torch.cuda.synchronize()
+    got = K.nhwc_to_nchw(out).cpu()
+    assert report("stem_rowk_%d" % size, got, ref) < (2e-4 if split else 2e-2)
+    check_stats(st.cpu(), ref)
+
+
+def test_heads_7x7(cuda):
+    x = rnd(2, 64, 64, 96, seed=10)
+    w_img, w_att = rnd(3, 64, 7, 7, seed=11, scale=0.02), rnd(1, 64, 7, 7, seed=12, scale=0.02)
+    ref = F.conv2d(x, torch.cat([w_img, w_att]), padding=3)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+    raw = K.conv7x7_heads_nhwc(xn, K.pack_head_weights(w_img.to(cuda), w_att.to(cuda)))
+    got = raw.permute(0, 3, 1, 2).cpu()
+    assert report("heads", got, ref) < 1e-5
+    bg = rnd(1, 3, 64, 96, seed=13)
+    color, mask, pred = K.heads_composite(raw, bg.to(cuda))
+    rc, rm = torch.tanh(ref[:, :3]), torch.sigmoid(ref[:, 3:])
+    assert (color.cpu() - rc).abs().max() < 1e-5 and (mask.cpu() - rm).abs().max() < 1e-5
+    assert (pred.cpu() - (rm * bg + (1 - rm) * rc)).abs().max() < 1e-5       # models/imitator.py:331
+
+
+def test_norm_act_warp(cuda):
+    """IN + ReLU + residual + LWB warp-add (networks/generator.py:13-20,283-295,303-320)."""
+    n, c, h, w = 3, 64, 32, 32
+    raw = rnd(n, c, h, w, seed=14) * 2 + 0.5
+    gamma, beta = 1 + 0.1 * rnd(c, seed=15), 0.1 * rnd(c, seed=16)
+    res = rnd(n, c, h, w, seed=17)
+    src = rnd(1, c, h, w, seed=18)
+    from impersonator_b200 import synthetic as S
+    T = S.synthetic_flow(n, 256, seed=3)
+    for ac in (False, True):
+        Ts = F.interpolate(T.permute(0, 3, 1, 2), size=(h, w), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        warp = F.grid_sample(src.expand(n, -1, -1, -1), Ts, mode="bilinear", padding_mode="zeros", align_corners=ac)
+        ref = F.relu(F.instance_norm(raw, weight=gamma, bias=beta, eps=1e-5)) + res + warp
+        nh = lambda t: t.permute(0, 2, 3, 1).contiguous().to(cuda)
+        raw_d = nh(raw)
+        st = K.instance_stats_nhwc(raw_d)
+        y = torch.empty_like(raw_d)
+        hi = torch.empty(raw_d.shape, dtype=torch.float16, device=cuda)
+        lo = torch.empty_like(hi)
+        ws = torch.empty((n, c, 2), dtype=torch.float32, device=cuda)
+        K.norm_act_nhwc(raw_d, st, gamma.to(cuda), beta.to(cuda), True, ws, residual=nh(res), warp_src=nh(src),
+                        T=T.to(cuda), align_corners=ac, y_f32=y, y_hi=hi, y_lo=lo)
+        got = y.permute(0, 3, 1, 2).cpu()
+        assert report("norm_act ac=%s" % ac, got, ref) < 2e-5
+        rec = (hi.float() + lo.float()).permute(0, 3, 1, 2).cpu()
+        assert (rec - got).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("ac", [False, True])
+def test_warp_nchw(cuda, ac):
+    from impersonator_b200 import synthetic as S
+    x = rnd(1, 24, 64, 64, seed=19)
+    T = S.synthetic_flow(2, 256, seed=4)
+    Ts = F.interpolate(T.permute(0, 3, 1, 2), size=(64, 64), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    ref = F.grid_sample(x.expand(2, -1, -1, -1), Ts, mode="bilinear", padding_mode="zeros", align_corners=ac)
+    got = K.warp_nchw(x.to(cuda), T.to(cuda), align_corners=ac).cpu()
+    assert report("transform", got, ref) < 2e-5
+    img = rnd(2, 3, 256, 256, seed=20)
+    ref2 = F.grid_sample(img, T, mode="bilinear", padding_mode="zeros", align_corners=ac)
+    got2 = K.warp_nchw(img.to(cuda), T.to(cuda), align_corners=ac).cpu()
+    assert report("stn", got2, ref2) < 2e-5
+
+
+def test_direct_conv(cuda):
+    x = rnd(1, 5, 40, 40, seed=21)
+    for (co, k, s, p, d) in ((8, 5, 1, 2, 1), (6, 4, 2, 1, 1), (7, 3, 1, 4, 4), (3, 1, 1, 0, 1)):
+        wt, b = rnd(co, 5, k, k, seed=22, scale=0.1), rnd(co, seed=23)
+        ref = F.conv2d(x, wt, b, stride=s, padding=p, dilation=d)
+        got = K.conv2d_direct_nchw(x.to(cuda), wt.to(cuda), b.to(cuda), stride=s, pad=p, dil=d).cpu()
+        assert report("direct k%d s%d d%d" % (k, s, d), got, ref) < 1e-5
