@@ -1,0 +1,577 @@
+"""Host-side mirror of networks/generator.py (the reference's generator), running on the
+B200-native conv engine behind the C ABI.
+
+Same class names, constructor arguments, method signatures and ``state_dict`` keys as the
+reference, so checkpoints (``BaseModel._load_params``, models/models.py:159-179) and callers
+(models/imitator.py, swapper.py, viewer.py) work unchanged:
+
+  ResidualBlock            networks/generator.py:8-20
+  ResNetGenerator          networks/generator.py:23-65     (BG net)
+  ResUnetGenerator         networks/generator.py:68-184    (SID / TSF nets)
+  ImpersonatorGenerator    networks/generator.py:187-320   (forward, encode_src, infer_front, swap,
+                                                            inference, resize_trans, stn, transform)
+
+The ``nn.Conv2d`` / ``nn.InstanceNorm2d`` / ``nn.ConvTranspose2d`` children are parameter holders
+only (they give the reference's key names and default init); every forward path goes through
+``_UnetStream`` / ``_ResnetStream`` below, which drive hand-written sm_100a kernels:
+tcgen05 implicit-GEMM convs (fp16 hi/lo split operands, fp32 accumulate), a fused
+InstanceNorm+ReLU+residual+Liquid-Warping-Block kernel, and the 7x7 heads.  There is no torch
+fallback: without the CUDA library the calls raise.
+
+Extensions over the reference (all optional): source features may have batch 1 while the target
+batch is B (torch's grid_sample cannot broadcast); ``LWB_PRECISION=fp16`` selects the
+single-pass "fast" mode (default ``fp16x3`` meets the 1e-3 parity bar); ``LWB_ALIGN_CORNERS=1``
+selects torch-1.2 grid_sample semantics (default 0 = installed-torch semantics = the oracle).
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from ._lib import LwbError
+
+
+def _split_mode():
+    mode = os.environ.get("LWB_PRECISION", "fp16x3")
+    if mode not in ("fp16x3", "fp16"):
+        raise LwbError("LWB_PRECISION must be fp16x3 or fp16")
+    return mode == "fp16x3"
+
+
+def _align_corners():
+    return os.environ.get("LWB_ALIGN_CORNERS", "0") == "1"
+
+
+class NetworkBase(nn.Module):
+    """networks/networks.py:45-80."""
+
+    def __init__(self):
+        super(NetworkBase, self).__init__()
+        self._name = 'BaseNetwork'
+
+    @property
+    def name(self):
+        return self._name
+
+    def init_weights(self):
+        self.apply(self._weights_init_fn)
+        self._lwb_invalidate()
+
+    def _weights_init_fn(self, m):
+        classname = m.__class__.__name__
+        if classname.find('Conv') != -1:
+            m.weight.data.normal_(0.0, 0.02)
+            if hasattr(m.bias, 'data'):
+                m.bias.data.fill_(0)
+        elif classname.find('BatchNorm2d') != -1:
+            m.weight.data.normal_(1.0, 0.02)
+            m.bias.data.fill_(0)
+
+    def _lwb_invalidate(self):
+        for m in self.modules():
+            if hasattr(m, '_lwb_streams'):
+                m._lwb_streams = {}
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super(NetworkBase, self).load_state_dict(*args, **kwargs)
+        self._lwb_invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super(NetworkBase, self)._apply(fn, *args, **kwargs)
+        self._lwb_invalidate()
+        return out
+
+
+class ResidualBlock(nn.Module):
+    """networks/generator.py:8-20 (parameter holder)."""
+
+    def __init__(self, dim_in, dim_out):
+        super(ResidualBlock, self).__init__()
+        self.main = nn.Sequential(
+            nn.Conv2d(dim_in, dim_out, kernel_size=3, stride=1, padding=1, bias=False),
+            nn.InstanceNorm2d(dim_out, affine=True),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(dim_out, dim_out, kernel_size=3, stride=1, padding=1, bias=False),
+            nn.InstanceNorm2d(dim_out, affine=True))
+
+    def forward(self, x):
+        raise LwbError("ResidualBlock runs only inside the fused generator streams")
+
+
+# ------------------------------------------------------------------------------------------
+# engine: one network bound to (batch, H, W, precision) -> persistent buffers + conv plans
+# ------------------------------------------------------------------------------------------
+class _Act(object):
+    """An activation: NHWC fp16 hi/lo operands for the next conv, optional fp32 copy."""
+    __slots__ = ("hi", "lo", "f32")
+
+    def __init__(self, shape, dev, split, want_f32=False, want_half=True):
+        self.hi = torch.empty(shape, dtype=torch.float16, device=dev) if want_half else None
+        self.lo = torch.empty(shape, dtype=torch.float16, device=dev) if (want_half and split) else None
+        self.f32 = torch.empty(shape, dtype=torch.float32, device=dev) if want_f32 else None
+
+    @property
+    def pair(self):
+        return (self.hi, self.lo)
+
+
+class _Layer(object):
+    """conv (+ InstanceNorm params) bound to buffers: plan + stats slot."""
+    __slots__ = ("plan", "raw", "stats", "gamma", "beta", "w")
+
+
+class _StreamBase(object):
+    def __init__(self, B, H, W, dev, split):
+        self.B, self.H, self.W, self.dev, self.split = B, H, W, dev, split
+        self._stats_slots = []
+        self._layers = []
+        self._raw = {}
+        self.ws = None
+
+    def _raw_buf(self, h, w, c):
+        key = (h, w, c)
+        if key not in self._raw:
+            self._raw[key] = torch.empty((self.B, h, w, c), dtype=torch.float32, device=self.dev)
+        return self._raw[key]
+
+    def _make_layer(self, conv, norm, x0, x1=None, stride=1, transposed=False, rowk=False, row_pitch=0, h=None, w=None):
+        L = _Layer()
+        wt = conv.weight.detach()
+        if rowk:
+            L.w = K.pack_conv_weight_rowk(wt, split=self.split)
+            cout, kh, kw = wt.shape[0], wt.shape[2], wt.shape[3]
+            d = K.make_conv_desc(self.B, h, w, 8, cout, kh, kw, stride=1, pad=kh // 2, split=self.split,
+                                 rowk=True, row_pitch=row_pitch)
+        else:
+            L.w = K.pack_conv_weight(wt, transposed=transposed, split=self.split)
+            cout = wt.shape[1] if transposed else wt.shape[0]
+            kh, kw = wt.shape[2], wt.shape[3]
+            cin0 = x0[0].shape[3]
+            cin1 = x1[0].shape[3] if x1 is not None else 0
+            d = K.make_conv_desc(self.B, h, w, cin0, cout, kh, kw, stride=stride, pad=conv.padding[0],
+                                 cin1=cin1, transposed=transposed, split=self.split)
+        L.raw = self._raw_buf(d.h_out, d.w_out, cout)
+        L.stats = (len(self._stats_slots), cout)
+        self._stats_slots.append(cout)
+        L.gamma = norm.weight.detach().float().contiguous() if norm is not None else None
+        L.beta = norm.bias.detach().float().contiguous() if norm is not None else None
+        L.plan = (d, x0, x1)
+        self._layers.append(L)
+        return L
+
+    def _finalize(self):
+        cmax = max(self._stats_slots)
+        self.stats = torch.zeros((len(self._stats_slots), self.B, cmax, 2), dtype=torch.float64, device=self.dev)
+        self.ws = torch.empty((self.B, cmax, 2), dtype=torch.float32, device=self.dev)
+        for L in self._layers:
+            slot, cout = L.stats
+            # per-layer contiguous [B, cout, 2] view at the head of the slot
+            L.stats = self.stats[slot].view(-1)[:self.B * cout * 2].view(self.B, cout, 2)
+            d, x0, x1 = L.plan
+            L.plan = K.ConvPlan(d, x0, x1, L.w, L.raw, L.stats)
+
+    def _conv_norm(self, L, out, relu, residual=None, warp_src=None, T=None, ac=False):
+        L.plan.run()
+        K.norm_act_nhwc(L.raw, L.stats, L.gamma, L.beta, relu, self.ws, residual=residual, warp_src=warp_src, T=T,
+                        align_corners=ac, y_f32=out.f32, y_hi=out.hi, y_lo=out.lo)
+
+
+class _UnetStream(_StreamBase):
+    """ResUnetGenerator (networks/generator.py:68-184) bound to fixed shapes."""
+
+    def __init__(self, net, B, H, W, dev, split, keep_f32=False):
+        super(_UnetStream, self).__init__(B, H, W, dev, split)
+        self.n_down, self.repeat = net.n_down, net.repeat_num
+        nd = self.n_down
+        if H % (1 << nd) or W % (1 << nd):
+            raise LwbError("image size must be divisible by %d" % (1 << nd))
+        self.keep_f32 = keep_f32
+        # stem input: padded NHWC8 (3 px border top/left/bottom, 5 right) for the row-K 7x7 conv
+        self.pitch = W + 8
+        self.x_pad = _Act((B, H + 6, self.pitch, 8), dev, split)
+        self.cin = net.encoders[0][0].weight.shape[1]
+        if self.cin > 8:
+            raise LwbError("stem supports at most 8 input channels")
+        # encoders
+        self.e, self.enc_layers = [], []
+        c, h, w = net.encoders[0][0].weight.shape[0], H, W
+        self.enc_layers.append(self._make_layer(net.encoders[0][0], net.encoders[0][1], self.x_pad.pair, rowk=True,
+                                                row_pitch=self.pitch, h=H, w=W))
+        self.e.append(_Act((B, h, w, c), dev, split, want_f32=keep_f32))
+        for i in range(1, nd + 1):
+            self.enc_layers.append(self._make_layer(net.encoders[i][0], net.encoders[i][1], self.e[i - 1].pair,
+                                                    stride=2, h=h, w=w))
+            c, h, w = c * 2, h // 2, w // 2
+            self.e.append(_Act((B, h, w, c), dev, split, want_f32=(keep_f32 or i == nd)))
+        # resnets (ping-pong x buffers; h buffer for the mid activation)
+        self.hb = _Act((B, h, w, c), dev, split)
+        self.res_layers, self.res_out = [], []
+        prev = self.e[nd]
+        for i in range(self.repeat):
+            out = _Act((B, h, w, c), dev, split, want_f32=True)
+            l1 = self._make_layer(net.resnets[i].main[0], net.resnets[i].main[1], prev.pair, h=h, w=w)
+            l2 = self._make_layer(net.resnets[i].main[3], net.resnets[i].main[4], self.hb.pair, h=h, w=w)
+            self.res_layers.append((l1, l2))
+            self.res_out.append(out)
+            prev = out
+        # decoders + skippers
+        self.dec_layers, self.d_up, self.d_out = [], [], []
+        for i in range(nd):
+            up = _Act((B, h * 2, w * 2, c // 2), dev, split)
+            ld = self._make_layer(net.decoders[i][0], net.decoders[i][1], prev.pair, stride=2, transposed=True, h=h, w=w)
+            c, h, w = c // 2, h * 2, w * 2
+            last = (i == nd - 1)
+            out = _Act((B, h, w, c), dev, split, want_f32=last, want_half=not last)
+            ls = self._make_layer(net.skippers[i][0], net.skippers[i][1], self.e[nd - 1 - i].pair, x1=up.pair, h=h, w=w)
+            self.dec_layers.append((ld, ls))
+            self.d_up.append(up)
+            self.d_out.append(out)
+            prev = out
+        self.w4 = K.pack_head_weights(net.img_reg[0].weight.detach(), net.attetion_reg[0].weight.detach())
+        self.head_raw = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        self._finalize()
+
+    # ---- pieces -------------------------------------------------------------------------
+    def load_input(self, x):
+        if tuple(x.shape) != (self.B, self.cin, self.H, self.W) or x.dtype != torch.float32:
+            raise LwbError("unexpected input %s (stream built for %s)" % (tuple(x.shape), (self.B, self.cin, self.H, self.W)))
+        K.nchw_to_nhwc_split(x.contiguous(), c_pad=8, pad_hw=(3, 3, 3, 5), hi=self.x_pad.hi, lo=self.x_pad.lo)
+
+    def encode(self, warp_srcs=None, T=None, ac=False, upto=None):
+        """encoders 0..n_down; warp_srcs[i] (NHWC fp32, i >= 1) is LWB-added after encoder i."""
+        self.stats.zero_()
+        self._conv_norm(self.enc_layers[0], self.e[0], True)
+        for i in range(1, self.n_down + 1):
+            src = warp_srcs[i] if warp_srcs is not None else None
+            if isinstance(src, (list, tuple)):          # swap(): two warps per site
+                self._conv_norm(self.enc_layers[i], self.e[i], True, warp_src=src[0][0], T=src[0][1], ac=ac)
+                self._add_warp(self.e[i], src[1][0], src[1][1], ac)
+            else:
+                self._conv_norm(self.enc_layers[i], self.e[i], True, warp_src=src, T=T, ac=ac)
+
+    def _add_warp(self, act, src, T, ac):
+        if act.f32 is None:
+            raise LwbError("second warp needs an fp32 activation")
+        K.norm_act_nhwc(act.f32, None, None, None, False, self.ws, warp_src=src, T=T, align_corners=ac,
+                        y_f32=act.f32, y_hi=act.hi, y_lo=act.lo)
+
+    def resnets(self, warp_srcs=None, T=None, ac=False):
+        x = self.e[self.n_down]
+        for i, (l1, l2) in enumerate(self.res_layers):
+            self._conv_norm(l1, self.hb, True)
+            src = warp_srcs[i] if warp_srcs is not None else None
+            if isinstance(src, (list, tuple)):
+                self._conv_norm(l2, self.res_out[i], False, residual=x.f32, warp_src=src[0][0], T=src[0][1], ac=ac)
+                self._add_warp(self.res_out[i], src[1][0], src[1][1], ac)
+            else:
+                self._conv_norm(l2, self.res_out[i], False, residual=x.f32, warp_src=src, T=T, ac=ac)
+            x = self.res_out[i]
+
+    def decode(self):
+        for i, (ld, ls) in enumerate(self.dec_layers):
+            self._conv_norm(ld, self.d_up[i], True)
+            self._conv_norm(ls, self.d_out[i], True)
+
+    def heads(self, bg=None, want_color=True, want_mask=True):
+        K.conv7x7_heads_nhwc(self.d_out[-1].f32, self.w4, out=self.head_raw)
+        return K.heads_composite(self.head_raw, bg, want_color=want_color, want_mask=want_mask)
+
+    def encoder_outs_nchw(self):
+        outs = []
+        for a in self.e:
+            t = K.nhwc_to_nchw(a.f32)
+            t._lwb_nhwc = a.f32.clone()
+            outs.append(t)
+        return outs
+
+    def resnet_outs_nchw(self):
+        outs = []
+        for a in self.res_out:
+            t = K.nhwc_to_nchw(a.f32)
+            t._lwb_nhwc = a.f32.clone()
+            outs.append(t)
+        return outs
+
+
+class _ResnetStream(_StreamBase):
+    """ResNetGenerator (networks/generator.py:23-65, the BG net) bound to fixed shapes."""
+
+    def __init__(self, net, B, H, W, dev, split):
+        super(_ResnetStream, self).__init__(B, H, W, dev, split)
+        layers = list(net.model)
+        nd, rep = net._n_down, net._repeat_num
+        self.pitch = W + 8
+        self.x_pad = _Act((B, H + 6, self.pitch, 8), dev, split)
+        self.cin = layers[0].weight.shape[1]
+        if self.cin > 8:
+            raise LwbError("stem supports at most 8 input channels")
+        self.seq = []
+        i = 0
+        c, h, w = layers[0].weight.shape[0], H, W
+        out = _Act((B, h, w, c), dev, split)
+        self.seq.append(("cn", self._make_layer(layers[0], layers[1], self.x_pad.pair, rowk=True, row_pitch=self.pitch, h=H, w=W), out, True, None))
+        prev = out
+        i += 3
+        for k in range(nd):
+            out = _Act((B, h // 2, w // 2, c * 2), dev, split, want_f32=(k == nd - 1))
+            self.seq.append(("cn", self._make_layer(layers[i], layers[i + 1], prev.pair, stride=2, h=h, w=w), out, True, None))
+            c, h, w = c * 2, h // 2, w // 2
+            prev = out
+            i += 3
+        hb = _Act((B, h, w, c), dev, split)
+        for k in range(rep):
+            blk = layers[i]
+            out = _Act((B, h, w, c), dev, split, want_f32=True)
+            self.seq.append(("cn", self._make_layer(blk.main[0], blk.main[1], prev.pair, h=h, w=w), hb, True, None))
+            self.seq.append(("cn", self._make_layer(blk.main[3], blk.main[4], hb.pair, h=h, w=w), out, False, prev))
+            prev = out
+            i += 1
+        for k in range(nd):
+            last = (k == nd - 1)
+            out = _Act((B, h * 2, w * 2, c // 2), dev, split, want_f32=last, want_half=not last)
+            self.seq.append(("cn", self._make_layer(layers[i], layers[i + 1], prev.pair, stride=2, transposed=True, h=h, w=w), out, True, None))
+            c, h, w = c // 2, h * 2, w * 2
+            prev = out
+            i += 3
+        self.final = prev
+        w_img = layers[i].weight.detach()
+        self.w4 = K.pack_head_weights(w_img, torch.zeros_like(w_img[:1]))
+        self.head_raw = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        self._finalize()
+
+    def run(self, x):
+        if tuple(x.shape) != (self.B, self.cin, self.H, self.W):
+            raise LwbError("unexpected input shape %s" % (tuple(x.shape),))
+        K.nchw_to_nhwc_split(x.float().contiguous(), c_pad=8, pad_hw=(3, 3, 3, 5), hi=self.x_pad.hi, lo=self.x_pad.lo)
+        self.stats.zero_()
+        for _, L, out, relu, res in self.seq:
+            self._conv_norm(L, out, relu, residual=(res.f32 if res is not None else None))
+        K.conv7x7_heads_nhwc(self.final.f32, self.w4, out=self.head_raw)
+        color, _, _ = K.heads_composite(self.head_raw, None, want_color=True, want_mask=False)
+        return color
+
+
+def _stream_for(mod, cls, key, *args, **kw):
+    streams = mod.__dict__.setdefault('_lwb_streams', {})
+    if key not in streams:
+        if len(streams) >= 4:
+            streams.clear()
+        streams[key] = cls(mod, *args, **kw)
+    return streams[key]
+
+
+def _nhwc_of(t):
+    """NHWC fp32 twin of an NCHW feature (cached on the tensor by encode_src / inference)."""
+    cached = getattr(t, '_lwb_nhwc', None)
+    if cached is not None:
+        return cached
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+class ResNetGenerator(NetworkBase):
+    """Generator. Encoder-Decoder Architecture (networks/generator.py:23-65)."""
+
+    def __init__(self, conv_dim=64, c_dim=5, repeat_num=9, k_size=4, n_down=2):
+        super(ResNetGenerator, self).__init__()
+        self._name = 'resnet_generator'
+        self._n_down, self._repeat_num = n_down, repeat_num
+        if k_size != 3:
+            raise LwbError("the B200 conv engine implements k_size=3 (what ImpersonatorGenerator uses)")
+        layers = []
+        layers.append(nn.Conv2d(c_dim, conv_dim, kernel_size=7, stride=1, padding=3, bias=False))
+        layers.append(nn.InstanceNorm2d(conv_dim, affine=True))
+        layers.append(nn.ReLU(inplace=True))
+        curr_dim = conv_dim
+        for i in range(n_down):
+            layers.append(nn.Conv2d(curr_dim, curr_dim * 2, kernel_size=k_size, stride=2, padding=1, bias=False))
+            layers.append(nn.InstanceNorm2d(curr_dim * 2, affine=True))
+            layers.append(nn.ReLU(inplace=True))
+            curr_dim = curr_dim * 2
+        for i in range(repeat_num):
+            layers.append(ResidualBlock(dim_in=curr_dim, dim_out=curr_dim))
+        for i in range(n_down):
+            layers.append(nn.ConvTranspose2d(curr_dim, curr_dim // 2, kernel_size=k_size, stride=2, padding=1,
+                                             output_padding=1, bias=False))
+            layers.append(nn.InstanceNorm2d(curr_dim // 2, affine=True))
+            layers.append(nn.ReLU(inplace=True))
+            curr_dim = curr_dim // 2
+        layers.append(nn.Conv2d(curr_dim, 3, kernel_size=7, stride=1, padding=3, bias=False))
+        layers.append(nn.Tanh())
+        self.model = nn.Sequential(*layers)
+
+    @torch.no_grad()
+    def forward(self, x, c=None):
+        if c is not None:
+            c = c.unsqueeze(2).unsqueeze(3)
+            c = c.expand(c.size(0), c.size(1), x.size(2), x.size(3))
+            x = torch.cat([x, c], dim=1)
+        B, _, H, W = x.shape
+        split = _split_mode()
+        st = _stream_for(self, _ResnetStream, ('bg', B, H, W, split), B, H, W, x.device, split)
+        return st.run(x)
+
+
+class ResUnetGenerator(NetworkBase):
+    """Generator. Encoder-Decoder Architecture (networks/generator.py:68-184)."""
+
+    def __init__(self, conv_dim=64, c_dim=5, repeat_num=6, k_size=4, n_down=2):
+        super(ResUnetGenerator, self).__init__()
+        self._name = 'resunet_generator'
+        self.repeat_num = repeat_num
+        self.n_down = n_down
+        if k_size != 3:
+            raise LwbError("the B200 conv engine implements k_size=3 (what ImpersonatorGenerator uses)")
+        encoders = []
+        encoders.append(nn.Sequential(
+            nn.Conv2d(c_dim, conv_dim, kernel_size=7, stride=1, padding=3, bias=False),
+            nn.InstanceNorm2d(conv_dim, affine=True),
+            nn.ReLU(inplace=True)))
+        curr_dim = conv_dim
+        for i in range(n_down):
+            encoders.append(nn.Sequential(
+                nn.Conv2d(curr_dim, curr_dim * 2, kernel_size=k_size, stride=2, padding=1, bias=False),
+                nn.InstanceNorm2d(curr_dim * 2, affine=True),
+                nn.ReLU(inplace=True)))
+            curr_dim = curr_dim * 2
+        self.encoders = nn.Sequential(*encoders)
+        resnets = []
+        for i in range(repeat_num):
+            resnets.append(ResidualBlock(dim_in=curr_dim, dim_out=curr_dim))
+        self.resnets = nn.Sequential(*resnets)
+        decoders, skippers = [], []
+        for i in range(n_down):
+            decoders.append(nn.Sequential(
+                nn.ConvTranspose2d(curr_dim, curr_dim // 2, kernel_size=k_size, stride=2, padding=1, output_padding=1, bias=False),
+                nn.InstanceNorm2d(curr_dim // 2, affine=True),
+                nn.ReLU(inplace=True)))
+            skippers.append(nn.Sequential(
+                nn.Conv2d(curr_dim, curr_dim // 2, kernel_size=k_size, stride=1, padding=1, bias=False),
+                nn.InstanceNorm2d(curr_dim // 2, affine=True),
+                nn.ReLU(inplace=True)))
+            curr_dim = curr_dim // 2
+        self.decoders = nn.Sequential(*decoders)
+        self.skippers = nn.Sequential(*skippers)
+        layers = []
+        layers.append(nn.Conv2d(curr_dim, 3, kernel_size=7, stride=1, padding=3, bias=False))
+        layers.append(nn.Tanh())
+        self.img_reg = nn.Sequential(*layers)
+        layers = []
+        layers.append(nn.Conv2d(curr_dim, 1, kernel_size=7, stride=1, padding=3, bias=False))
+        layers.append(nn.Sigmoid())
+        self.attetion_reg = nn.Sequential(*layers)
+
+    def _stream(self, x, keep_f32, tag):
+        B, _, H, W = x.shape
+        split = _split_mode()
+        return _stream_for(self, _UnetStream, (tag, B, H, W, split, keep_f32), B, H, W, x.device, split, keep_f32=keep_f32)
+
+    @torch.no_grad()
+    def inference(self, x):
+        """encoder_outs [4], resnet_outs [6] as NCHW fp32 (networks/generator.py:136-147)."""
+        st = self._stream(x, True, 'inference')
+        st.load_input(x.float())
+        st.encode()
+        st.resnets()
+        return st.encoder_outs_nchw(), st.resnet_outs_nchw()
+
+    @torch.no_grad()
+    def forward(self, x):
+        st = self._stream(x, False, 'forward')
+        st.load_input(x.float())
+        st.encode()
+        st.resnets()
+        st.decode()
+        color, mask, _ = st.heads()
+        return color, mask
+
+    def encode(self, x):
+        return self.inference(x)[0]
+
+    def decode(self, x, encoder_outs):
+        raise LwbError("decode() on detached tensors is not part of the inference hot path; use forward()/inference()")
+
+    def regress(self, x):
+        raise LwbError("regress() on detached tensors is not part of the inference hot path; use forward()")
+
+
+class ImpersonatorGenerator(NetworkBase):
+    """Generator. Encoder-Decoder Architecture (networks/generator.py:187-320)."""
+
+    def __init__(self, bg_dim, src_dim, tsf_dim, conv_dim=64, repeat_num=6):
+        super(ImpersonatorGenerator, self).__init__()
+        self._name = 'impersonator_generator'
+        self.n_down = 3
+        self.repeat_num = repeat_num
+        self.bg_model = ResNetGenerator(conv_dim=conv_dim, c_dim=bg_dim, repeat_num=repeat_num, k_size=3, n_down=self.n_down)
+        self.src_model = ResUnetGenerator(conv_dim=conv_dim, c_dim=src_dim, repeat_num=repeat_num, k_size=3, n_down=self.n_down)
+        self.tsf_model = ResUnetGenerator(conv_dim=conv_dim, c_dim=tsf_dim, repeat_num=repeat_num, k_size=3, n_down=self.n_down)
+
+    @torch.no_grad()
+    def forward(self, bg_inputs, src_inputs, tsf_inputs, T):
+        img_bg = self.bg_model(bg_inputs)
+        src_img, src_mask, tsf_img, tsf_mask = self.infer_front(src_inputs, tsf_inputs, T)
+        return img_bg, src_img, src_mask, tsf_img, tsf_mask
+
+    def encode_src(self, src_inputs):
+        return self.src_model.inference(src_inputs)
+
+    @torch.no_grad()
+    def infer_front(self, src_inputs, tsf_inputs, T):
+        ac = _align_corners()
+        T = T.float().contiguous()
+        src = self.src_model._stream(src_inputs, True, 'front')
+        src.load_input(src_inputs.float())
+        src.encode()
+        src.resnets()
+        tsf = self.tsf_model._stream(tsf_inputs, False, 'front')
+        tsf.load_input(tsf_inputs.float())
+        tsf.encode(warp_srcs=[None] + [a.f32 for a in src.e[1:]], T=T, ac=ac)
+        tsf.resnets(warp_srcs=[a.f32 for a in src.res_out], T=T, ac=ac)
+        src.decode()
+        src_img, src_mask, _ = src.heads()
+        tsf.decode()
+        tsf_img, tsf_mask, _ = tsf.heads()
+        return src_img, src_mask, tsf_img, tsf_mask
+
+    @torch.no_grad()
+    def swap(self, tsf_inputs, src_encoder_outs12, src_encoder_outs21, src_resnet_outs12, src_resnet_outs21, T12, T21):
+        ac = _align_corners()
+        T12, T21 = T12.float().contiguous(), T21.float().contiguous()
+        tsf = self.tsf_model._stream(tsf_inputs, True, 'swap')
+        tsf.load_input(tsf_inputs.float())
+        enc = [None] + [((_nhwc_of(a), T12), (_nhwc_of(b), T21)) for a, b in zip(src_encoder_outs12[1:], src_encoder_outs21[1:])]
+        res = [((_nhwc_of(a), T12), (_nhwc_of(b), T21)) for a, b in zip(src_resnet_outs12, src_resnet_outs21)]
+        tsf.encode(warp_srcs=enc, ac=ac)
+        tsf.resnets(warp_srcs=res, ac=ac)
+        tsf.decode()
+        tsf_img, tsf_mask, _ = tsf.heads()
+        return tsf_img, tsf_mask
+
+    @torch.no_grad()
+    def inference(self, src_encoder_outs, src_resnet_outs, tsf_inputs, T, bg=None):
+        """networks/generator.py:277-301.  With ``bg`` also returns the composite of
+        models/imitator.py:331 as a third value (fused into the head kernel)."""
+        ac = _align_corners()
+        tsf = self.tsf_model._stream(tsf_inputs, False, 'inference')
+        tsf.load_input(tsf_inputs.float())
+        T = T.float().contiguous()
+        tsf.encode(warp_srcs=[None] + [_nhwc_of(a) for a in src_encoder_outs[1:]], T=T, ac=ac)
+        tsf.resnets(warp_srcs=[_nhwc_of(a) for a in src_resnet_outs], T=T, ac=ac)
+        tsf.decode()
+        color, mask, pred = tsf.heads(bg)
+        if bg is not None:
+            return color, mask, pred
+        return color, mask
+
+    def resize_trans(self, x, T):
+        raise LwbError("resize_trans is fused into the warp kernels; call transform()/stn()")
+
+    @torch.no_grad()
+    def stn(self, x, T):
+        return K.warp_nchw(x.float().contiguous(), T.float().contiguous(), align_corners=_align_corners())
+
+    @torch.no_grad()
+    def transform(self, x, T):
+        return K.warp_nchw(x.float().contiguous(), T.float().contiguous(), align_corners=_align_corners())

@@ -1,0 +1,298 @@
+"""Host-side mirror of models/imitator.py's ``Imitator`` (motion imitation, inference only).
+
+Keeps the reference's public surface so ``run_imitator.py`` drives it unchanged:
+
+  Imitator(opt)                                                         models/imitator.py:14-46
+  personalize(src_path, src_smpl=None, output_path='', visualizer=None) :82-145
+  inference(tgt_paths, tgt_smpls=None, cam_strategy='smooth', output_dir='', visualizer=None, verbose=True)
+      -> list of float32 HxWx3 arrays in [-1, 1]                         :157-189
+  inference_by_smpls(tgt_smpls, cam_strategy='smooth', output_dir='', visualizer=None)   :192-214
+  swap_smpl / transfer_params_by_smpl / transfer_params / forward / warp_front           :216-342
+  public state ``src_info`` / ``tsf_info`` (read by run_imitator.write_pair_info, run_imitator.py:33-45)
+
+What changes is how the per-frame work executes: the reference loops over frames at batch 1,
+launching >100 small kernels and syncing on ``.cpu()`` every frame (:166-179); here frames are
+processed ``opt.batch_size`` at a time -- one fused correspondence pass (raster + cond + T + image
+warp), one generator pass on the tcgen05 conv engine, one device->host copy per chunk -- and the
+results are returned per frame, in order, with ``tsf_info`` describing the last frame.
+
+Out of scope: HMR / SMPL (``networks/hmr.py``; need external model files) --
+any object with ``__call__(img) -> theta`` and ``get_details(theta) -> {cam, pose, shape, verts, ...}``
+can be injected as ``hmr``; ``post_personalize`` (fine-tuning, needs backward); Mask-RCNN detector.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from ._lib import LwbError
+from .generator import ImpersonatorGenerator
+from .nmr import SMPLRenderer
+
+
+def morph(src_bg_mask, ks, mode='erode'):
+    """utils/util.py:73-89: box-filter erode / dilate of a {0,1} mask [N,1,H,W] (border counts as 1 / 0)."""
+    pad = ks // 2
+    x = torch.nn.functional.pad(src_bg_mask, [pad, pad, pad, pad], value=1.0 if mode == 'erode' else 0.0)
+    pooled = torch.nn.functional.avg_pool2d(x, ks, stride=1) * (ks * ks)
+    if mode == 'erode':
+        return (pooled.round() == ks * ks).float()
+    return (pooled.round() >= 1).float()
+
+
+def _read_image(path, image_size):
+    """cv_utils.read_cv2_img + transform_img (utils/cv_utils.py:10-47) -> RGB float32 CHW in [0,1], original."""
+    import cv2
+    img = cv2.imread(path, -1)
+    if img is None:
+        raise IOError("cannot read %s" % path)
+    img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    x = cv2.resize(img, (image_size, image_size)).astype(np.float32) / 255.0
+    return x.transpose((2, 0, 1)), img
+
+
+def _save_image(img, path, image_size=None, normalize=False):
+    """cv_utils.save_cv2_img (utils/cv_utils.py:23-36)."""
+    import cv2
+    img = cv2.cvtColor(img, cv2.COLOR_RGB2BGR)
+    if image_size is not None:
+        img = cv2.resize(img, (image_size, image_size))
+    if normalize:
+        img = ((img + 1) / 2.0 * 255).astype(np.uint8)
+    cv2.imwrite(path, img)
+
+
+class Imitator(object):
+    def __init__(self, opt, generator=None, bgnet=None, hmr=None, render=None, device=None):
+        self._name = 'Imitator'
+        self._opt = opt
+        self.device = torch.device(device if device is not None else 'cuda')
+        self._G_cond_nc = getattr(opt, 'cond_nc', 3)
+        self.generator = (generator if generator is not None else self._create_generator()).to(self.device).eval()
+        bg_model = getattr(opt, 'bg_model', 'ORIGINAL')
+        if bgnet is not None:
+            self.bgnet = bgnet.to(self.device).eval()
+        elif bg_model == 'ORIGINAL':
+            self.bgnet = self.generator.bg_model
+        else:
+            from .inpaintor import InpaintSANet
+            self.bgnet = InpaintSANet(c_dim=4)
+            self._load_params(self.bgnet, bg_model)
+            self.bgnet = self.bgnet.to(self.device).eval()
+        self.hmr = hmr
+        if render is None:
+            raise LwbError("pass render=SMPLRenderer(...) (the SMPL face/uv assets are external downloads)")
+        self.render = render.to(self.device)
+        self.detector = None
+        self.src_info = None
+        self.tsf_info = None
+        self.first_cam = None
+
+    # ---- construction helpers (models/imitator.py:54-67, models/models.py:159-179) -------------
+    def _create_generator(self):
+        net = ImpersonatorGenerator(bg_dim=4, src_dim=3 + self._G_cond_nc, tsf_dim=3 + self._G_cond_nc,
+                                    repeat_num=getattr(self._opt, 'repeat_num', 6))
+        path = getattr(self._opt, 'load_path', '')
+        if path:
+            self._load_params(net, path)
+        return net
+
+    @staticmethod
+    def _load_params(net, path, need_module=False):
+        sd = torch.load(path, map_location='cpu')
+        if not need_module:
+            sd = {(k[7:] if k.startswith('module.') else k): v for k, v in sd.items()}
+        net.load_state_dict(sd)
+
+    @property
+    def _ac(self):
+        return os.environ.get("LWB_ALIGN_CORNERS", "0") == "1"
+
+    def _details(self, smpl):
+        if self.hmr is None:
+            raise LwbError("no body model: inject hmr= (HMR/SMPL need external files and are outside the hot path)")
+        return self.hmr.get_details(smpl)
+
+    # ---- personalize (models/imitator.py:82-145) ----------------------------------------------
+    @torch.no_grad()
+    def personalize(self, src_path, src_smpl=None, output_path='', visualizer=None, src_img=None):
+        size = self._opt.image_size
+        if src_img is None:
+            img, ori_img = _read_image(src_path, size)
+            img = torch.tensor(img * 2 - 1.0, dtype=torch.float32, device=self.device)[None, ...]
+        else:
+            img, ori_img = src_img.to(self.device).float(), None
+        if src_smpl is None:
+            if self.hmr is None or ori_img is None:
+                raise LwbError("src_smpl required when no HMR network is injected")
+            import cv2
+            img_hmr = cv2.resize(ori_img, (224, 224)).astype(np.float32).transpose((2, 0, 1)) / 255.0 * 2 - 1.0
+            src_smpl = self.hmr(torch.tensor(img_hmr, dtype=torch.float32, device=self.device)[None, ...])
+        else:
+            src_smpl = torch.as_tensor(src_smpl, dtype=torch.float32, device=self.device).reshape(1, -1)
+
+        src_info = self._details(src_smpl)
+        tabs = self.render.correspond(src_info['cam'], src_info['verts'], None, None, want_f2verts=True)
+        src_info['fim'] = tabs['fim']
+        src_info['wim'] = tabs['wim']
+        src_info['cond'] = tabs['cond'].contiguous()
+        src_info['f2verts'] = tabs['f2verts']
+        p2verts = tabs['f2verts'][:, :, :, 0:2].clone()
+        p2verts[:, :, :, 1] *= -1                                       # models/imitator.py:105-107
+        src_info['p2verts'] = p2verts.contiguous()
+        if getattr(self._opt, 'only_vis', False):
+            src_info['p2verts'] = self.render.get_vis_f2pts(src_info['p2verts'], tabs['fim']).contiguous()
+        src_info['img'] = img
+        src_info['image'] = ori_img
+
+        bg_mask = morph(src_info['cond'][:, -1:, :, :], ks=getattr(self._opt, 'bg_ks', 13), mode='erode')
+        body_mask = 1 - bg_mask
+        if self.bgnet is self.generator.bg_model:
+            bg_inputs = torch.cat([img * bg_mask, bg_mask], dim=1)
+            src_info['bg'] = self.bgnet(bg_inputs)
+        else:
+            src_info['bg'] = self.bgnet(img, masks=body_mask, only_x=True)
+        ft_mask = 1 - morph(src_info['cond'][:, -1:, :, :], ks=getattr(self._opt, 'ft_ks', 3), mode='erode')
+        src_inputs = torch.cat([img * ft_mask, src_info['cond']], dim=1)
+        src_info['feats'] = self.generator.encode_src(src_inputs)
+        self.src_info = src_info
+        if visualizer is not None:
+            visualizer.vis_named_img('src', img)
+            visualizer.vis_named_img('bg', src_info['bg'])
+        if output_path and ori_img is not None:
+            _save_image(ori_img, output_path, image_size=size)
+
+    # ---- per-frame geometry (models/imitator.py:216-268) --------------------------------------
+    def swap_smpl(self, src_cam, src_shape, tgt_smpl, cam_strategy='smooth'):
+        tgt_cam = tgt_smpl[:, 0:3].contiguous()
+        pose = tgt_smpl[:, 3:75].contiguous()
+        if cam_strategy == 'smooth':
+            cam = src_cam.expand(tgt_smpl.shape[0], -1).clone()
+            cam[:, 1:] += tgt_cam[:, 1:] - self.first_cam[:, 1:]
+        elif cam_strategy == 'source':
+            cam = src_cam.expand(tgt_smpl.shape[0], -1)
+        else:
+            cam = tgt_cam
+        return torch.cat([cam, pose, src_shape.expand(tgt_smpl.shape[0], -1)], dim=1)
+
+    @torch.no_grad()
+    def transfer_params_by_smpl(self, tgt_smpl, cam_strategy='smooth', t=0):
+        """tgt_smpl [85] or [B,85]: one frame (reference) or a chunk of frames (batched fast path)."""
+        src_info = self.src_info
+        tgt_smpl = torch.as_tensor(tgt_smpl, dtype=torch.float32, device=self.device)
+        if tgt_smpl.dim() == 1:
+            tgt_smpl = tgt_smpl[None, ...]
+        if t == 0 and cam_strategy == 'smooth':
+            self.first_cam = tgt_smpl[0:1, 0:3].clone()
+        tsf_smpl = self.swap_smpl(src_info['cam'], src_info['shape'], tgt_smpl, cam_strategy=cam_strategy)
+        tsf_info = self._details(tsf_smpl)
+        out = self.render.correspond(tsf_info['cam'], tsf_info['verts'], src_info['p2verts'], src_info['img'],
+                                     align_corners=self._ac)
+        tsf_info['fim'] = out['fim']
+        tsf_info['wim'] = out['wim']
+        tsf_info['cond'] = out['cond']
+        tsf_info['tsf_img'] = out['tsf_img']
+        tsf_info['T'] = out['T']
+        self.tsf_info = tsf_info
+        return out['tsf_inputs']
+
+    @torch.no_grad()
+    def transfer_params(self, tgt_path, tgt_smpl=None, cam_strategy='smooth', t=0):
+        ori_img = None
+        if tgt_path:
+            _, ori_img = _read_image(tgt_path, self._opt.image_size)
+        if tgt_smpl is None:
+            if self.hmr is None or ori_img is None:
+                raise LwbError("tgt_smpl required when no HMR network is injected")
+            import cv2
+            img_hmr = cv2.resize(ori_img, (224, 224)).astype(np.float32).transpose((2, 0, 1)) / 255.0 * 2 - 1.0
+            tgt_smpl = self.hmr(torch.tensor(img_hmr, dtype=torch.float32, device=self.device)[None, ...])
+        tsf_inputs = self.transfer_params_by_smpl(tgt_smpl=tgt_smpl, cam_strategy=cam_strategy, t=t)
+        self.tsf_info['image'] = ori_img
+        return tsf_inputs
+
+    # ---- generator + composite (models/imitator.py:326-342) -----------------------------------
+    @torch.no_grad()
+    def forward(self, tsf_inputs, T):
+        enc, res = self.src_info['feats']
+        color, mask, pred = self.generator.inference(enc, res, tsf_inputs, T, bg=self.src_info['bg'])
+        if getattr(self._opt, 'front_warp', False):
+            pred = self.warp_front(pred, mask)
+        return pred
+
+    def warp_front(self, preds, mask):
+        front_mask = self.render.encode_front_fim(self.tsf_info['fim'], transpose=True, front_fn=True)
+        return (1 - front_mask) * preds + self.tsf_info['tsf_img'] * front_mask * (1 - mask)
+
+    # ---- the hot loop (models/imitator.py:157-214), chunked -----------------------------------
+    def _chunks(self, n):
+        bs = max(1, int(getattr(self._opt, 'batch_size', 1)))
+        return [(i, min(n, i + bs)) for i in range(0, n, bs)]
+
+    @torch.no_grad()
+    def inference(self, tgt_paths, tgt_smpls=None, cam_strategy='smooth', output_dir='', visualizer=None, verbose=True):
+        length = len(tgt_paths)
+        outputs = []
+        if tgt_smpls is None:
+            # frames come through HMR one by one (reference behaviour); still one sync per frame only
+            for t in range(length):
+                tsf_inputs = self.transfer_params(tgt_paths[t], None, cam_strategy, t=t)
+                preds = self.forward(tsf_inputs, self.tsf_info['T'])
+                outputs.append(preds[0].permute(1, 2, 0).cpu().numpy())
+                self._maybe_save(outputs[-1], tgt_paths[t], output_dir, t)
+            return outputs
+        for (a, b) in self._chunks(length):
+            smpls = torch.as_tensor(np.stack([np.asarray(s, dtype=np.float32) for s in tgt_smpls[a:b]]))
+            tsf_inputs = self.transfer_params_by_smpl(smpls, cam_strategy, t=a)
+            preds = self.forward(tsf_inputs, self.tsf_info['T'])
+            if visualizer is not None:
+                visualizer.vis_named_img('pred_' + cam_strategy, preds)
+            host = preds.permute(0, 2, 3, 1).contiguous().cpu().numpy()        # one D2H + sync per chunk
+            for j in range(b - a):
+                outputs.append(host[j])
+                self._maybe_save(host[j], tgt_paths[a + j], output_dir, a + j)
+        self._last_frame_info()
+        return outputs
+
+    @torch.no_grad()
+    def inference_by_smpls(self, tgt_smpls, cam_strategy='smooth', output_dir='', visualizer=None):
+        return self.inference([''] * len(tgt_smpls), tgt_smpls, cam_strategy, output_dir, visualizer, verbose=False)
+
+    def _last_frame_info(self):
+        """tsf_info must describe the LAST frame (run_imitator.py:33-45 reads fim/T/tsf_img/cam/verts/wim)."""
+        info = self.tsf_info
+        for k, v in list(info.items()):
+            if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] > 1:
+                info[k] = v[-1:]
+
+    def _maybe_save(self, pred, tgt_path, output_dir, t):
+        if not output_dir:
+            return
+        name = os.path.split(tgt_path)[-1] if tgt_path else 'pred_%.8d.jpg' % t
+        _save_image(pred, os.path.join(output_dir, 'pred_' + name if tgt_path else name), normalize=True)
+
+    def post_personalize(self, *a, **k):
+        raise LwbError("post_personalize (fine-tuning) needs the backward pass: outside the inference hot path")
+
+
+class SyntheticBodyModel(object):
+    """Stand-in for ``HumanModelRecovery.get_details`` (networks/hmr.py:302-330) when SMPL's model files
+    are absent: theta[0:3] = cam, theta[3:6] = (ry, rx, k) pose parameters of the synthetic UV-sphere
+    body (impersonator_b200.synthetic), theta[75:85] = shape (ignored)."""
+
+    def __init__(self, base_verts):
+        self.base = base_verts
+
+    def get_details(self, theta):
+        dev = theta.device
+        base = self.base.to(dev)
+        cam = theta[:, 0:3].contiguous()
+        ry, rx = theta[:, 3], theta[:, 4]
+        cy, sy, cx, sx = torch.cos(ry), torch.sin(ry), torch.cos(rx), torch.sin(rx)
+        zeros, ones = torch.zeros_like(cy), torch.ones_like(cy)
+        Ry = torch.stack([cy, zeros, sy, zeros, ones, zeros, -sy, zeros, cy], dim=1).view(-1, 3, 3)
+        Rx = torch.stack([ones, zeros, zeros, zeros, cx, -sx, zeros, sx, cx], dim=1).view(-1, 3, 3)
+        verts = base[None] @ Ry.transpose(1, 2) @ Rx.transpose(1, 2)
+        return {'theta': theta, 'cam': cam, 'pose': theta[:, 3:75].contiguous(), 'shape': theta[:, 75:].contiguous(),
+                'verts': verts.contiguous(), 'j2d': None, 'j3d': None}
