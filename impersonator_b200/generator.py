@@ -353,6 +353,21 @@ class _ResnetStream(_StreamBase):
         return color
 
 
+def profile_streams(warm_fn, run_fn):
+    """Instrumented passes: CUDA events around every kernel class (bench.py roofline / breakdown).
+    -> {"passes": n, "conv": {"ms", "flops", "n"}, "norm": {"ms", "bytes", "n"}, "heads"/"correspond"/"input": {"ms", ...}}"""
+    warm_fn()
+    torch.cuda.synchronize()
+    K.profile_begin()
+    n = len(run_fn())
+    raw = K.profile_end()
+    out = {"passes": n}
+    for cls in ("conv", "norm", "heads", "correspond", "input"):
+        r = raw.get(cls, {"ms": 0.0, "work": 0.0, "n": 0})
+        out[cls] = {"ms": r["ms"], "n": r["n"], ("flops" if cls in ("conv", "heads") else "bytes"): r["work"]}
+    return out
+
+
 def _stream_for(mod, cls, key, *args, **kw):
     streams = mod.__dict__.setdefault('_lwb_streams', {})
     if key not in streams:

@@ -248,7 +248,7 @@ class Imitator(object):
             preds = self.forward(tsf_inputs, self.tsf_info['T'])
             if visualizer is not None:
                 visualizer.vis_named_img('pred_' + cam_strategy, preds)
-            host = preds.permute(0, 2, 3, 1).contiguous().cpu().numpy()        # one D2H + sync per chunk
+            host = self._to_host(preds.permute(0, 2, 3, 1).contiguous())       # one D2H + sync per chunk
             for j in range(b - a):
                 outputs.append(host[j])
                 self._maybe_save(host[j], tgt_paths[a + j], output_dir, a + j)
@@ -258,6 +258,14 @@ class Imitator(object):
     @torch.no_grad()
     def inference_by_smpls(self, tgt_smpls, cam_strategy='smooth', output_dir='', visualizer=None):
         return self.inference([''] * len(tgt_smpls), tgt_smpls, cam_strategy, output_dir, visualizer, verbose=False)
+
+    @staticmethod
+    def _to_host(t):
+        """Device -> pinned host (torch's caching host allocator), one async copy + one sync."""
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h.numpy()
 
     def _last_frame_info(self):
         """tsf_info must describe the LAST frame (run_imitator.py:33-45 reads fim/T/tsf_img/cam/verts/wim)."""

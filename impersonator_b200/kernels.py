@@ -17,6 +17,60 @@ NEAR, FAR = 0.1, 100.0              # rasterize.py:10-11 defaults (what render_f
 
 _ws_cache = {}
 
+# ---- instrumentation: launch counter (bench.py "gpu_launches") and optional CUDA-event profiling ----
+_launches = 0
+_profile = None            # None, or {class: [(start_event, end_event, work), ...]}
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n):
+    global _launches
+    _launches += n
+
+
+class _Prof(object):
+    """with _Prof('conv', flops): ... -> CUDA events on the launching stream when profiling is on."""
+
+    def __init__(self, cls, work=0.0):
+        self.cls, self.work = cls, work
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _profile is not None:
+            self.e1.record()
+            _profile.setdefault(self.cls, []).append((self.e0, self.e1, self.work))
+        return False
+
+
+def profile_begin():
+    global _profile
+    _profile = {}
+
+
+def profile_end():
+    """-> {class: {"ms": total, "work": total, "n": launches}}"""
+    global _profile
+    torch.cuda.synchronize()
+    out = {}
+    for cls, items in (_profile or {}).items():
+        out[cls] = {"ms": sum(a.elapsed_time(b) for a, b, _ in items), "work": sum(w for _, _, w in items), "n": len(items)}
+    _profile = None
+    return out
+
 
 def _workspace(nbytes, device):
     key = (device.index, "raster")
@@ -66,7 +120,11 @@ def correspond(cam, verts, face_idx, image_size, map_fn, src_p2verts, src_img=No
                    tsf_inputs=torch.empty((B, 3 + C, s, s), dtype=torch.float32, device=dev),
                    f2verts=torch.empty((B, F, 3, 3), dtype=torch.float32, device=dev) if want_f2verts else None)
     ws = _workspace(lib().lwb_raster_workspace_bytes(B, s), dev)
-    check(lib().lwb_correspond(
+    _count(2)
+    # algorithmic bytes: per frame verts + fim/wim/T/tsf_inputs; per batch the shared tables
+    nbytes = B * (V * 12 + s * s * (4 + 12 + 8 + 4 * (3 + C))) + F * 12 + sb * F * 24 + (F + 1) * C * 4 + sb * 3 * s * s * 4
+    with _Prof("correspond", nbytes):
+      check(lib().lwb_correspond(
         ptr(cam), ptr(verts), ptr(face_idx), B, V, F, s, near, far, EYE_Z,
         ptr(map_fn), C, ptr(src_p2verts), ptr(src_img), sb, 1 if align_corners else 0,
         ptr(out["fim"]), ptr(out["wim"]), ptr(out["T"]), ptr(out["tsf_inputs"]), ptr(out.get("f2verts")),
@@ -130,8 +188,10 @@ def nchw_to_nhwc_split(x, c_pad=None, pad_hw=(0, 0, 0, 0), hi=None, lo=None, spl
     if hi is None:
         hi = torch.empty((n, hp, wp, c_pad), dtype=torch.float16, device=x.device)
         lo = torch.empty_like(hi) if split else None
-    check(lib().lwb_nchw_to_nhwc_split(ptr(x), n, c, h, w, c_pad, hp, wp, top, left, ptr(hi), ptr(lo), stream()),
-          "lwb_nchw_to_nhwc_split")
+    _count(1)
+    with _Prof("input", n * c * h * w * 4 + n * hp * wp * c_pad * (4 if lo is not None else 2)):
+        check(lib().lwb_nchw_to_nhwc_split(ptr(x), n, c, h, w, c_pad, hp, wp, top, left, ptr(hi), ptr(lo), stream()),
+              "lwb_nchw_to_nhwc_split")
     return hi, lo
 
 
@@ -159,9 +219,18 @@ class ConvPlan(object):
               "lwb_conv_plan_create")
         self._h = handle
         self.num_launches = lib().lwb_conv_plan_num_launches(handle)
+        d = desc
+        if d.transposed:       # algorithmic 2*MAC: every input pixel meets every (tap, cin, cout)
+            self.flops = 2.0 * d.n * d.h_in * d.w_in * d.cin0 * d.cout * d.kh * d.kw
+        elif d.rowk:
+            self.flops = 2.0 * d.n * d.h_out * d.w_out * d.cout * w[0].shape[0] * 7 * getattr(self, "_real_cin", 6)
+        else:
+            self.flops = 2.0 * d.n * d.h_out * d.w_out * d.cout * (d.cin0 + d.cin1) * d.kh * d.kw
 
     def run(self):
-        check(lib().lwb_conv_plan_run(self._h, stream()), "lwb_conv_plan_run")
+        _count(self.num_launches)
+        with _Prof("conv", self.flops):
+            check(lib().lwb_conv_plan_run(self._h, stream()), "lwb_conv_plan_run")
 
     def __del__(self):
         try:
@@ -204,9 +273,14 @@ def norm_act_nhwc(raw, stats, gamma, beta, relu, ws, eps=1e-5, residual=None, wa
     if warp_src is not None:
         sb = warp_src.shape[0]
         th, tw = T.shape[1:3]
-    check(lib().lwb_norm_act_nhwc(ptr(raw), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if relu else 0, n, h, w, c,
-                                  ptr(residual), ptr(warp_src), sb, ptr(T), th, tw, 1 if align_corners else 0,
-                                  ptr(ws), ptr(y_f32), ptr(y_hi), ptr(y_lo), stream()), "lwb_norm_act_nhwc")
+    _count(2 if stats is not None else 1)
+    per = 4 + (4 if residual is not None else 0) + (4 if y_f32 is not None else 0) \
+        + (2 if y_hi is not None else 0) + (2 if y_lo is not None else 0)
+    nbytes = n * h * w * c * per + (warp_src.numel() * 4 + n * h * w * 8 if warp_src is not None else 0)
+    with _Prof("norm", nbytes):
+        check(lib().lwb_norm_act_nhwc(ptr(raw), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if relu else 0, n, h, w, c,
+                                      ptr(residual), ptr(warp_src), sb, ptr(T), th, tw, 1 if align_corners else 0,
+                                      ptr(ws), ptr(y_f32), ptr(y_hi), ptr(y_lo), stream()), "lwb_norm_act_nhwc")
 
 
 def pack_head_weights(w_img, w_att):
@@ -224,7 +298,9 @@ def conv7x7_heads_nhwc(x, w4, out=None):
         raise LwbError("heads expect 64 input channels")
     if out is None:
         out = torch.empty((n, h, w, 4), dtype=torch.float32, device=x.device)
-    check(lib().lwb_conv7x7_heads_nhwc(ptr(x), ptr(w4), n, h, w, ptr(out), stream()), "lwb_conv7x7_heads_nhwc")
+    _count(1)
+    with _Prof("heads", 2.0 * n * h * w * 49 * 64 * 4):
+        check(lib().lwb_conv7x7_heads_nhwc(ptr(x), ptr(w4), n, h, w, ptr(out), stream()), "lwb_conv7x7_heads_nhwc")
     return out
 
 
@@ -238,8 +314,10 @@ def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, m
         mask = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
     if pred is None and bg is not None:
         pred = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
-    check(lib().lwb_heads_composite(ptr(raw), n, h, w, cs, ptr(bg), bg.shape[0] if bg is not None else 0,
-                                    ptr(color), ptr(mask), ptr(pred), stream()), "lwb_heads_composite")
+    _count(1)
+    with _Prof("heads", 0.0):
+        check(lib().lwb_heads_composite(ptr(raw), n, h, w, cs, ptr(bg), bg.shape[0] if bg is not None else 0,
+                                        ptr(color), ptr(mask), ptr(pred), stream()), "lwb_heads_composite")
     return color, mask, pred
 
 

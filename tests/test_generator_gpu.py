@@ -1,0 +1,99 @@
+"""End-to-end GPU parity of the generator mirror (tcgen05 conv engine + fused LWB) against
+  * the slices the REFERENCE modules produced (tests/golden/generator.npz), and
+  * the full outputs of the functional restatement (oracle/generator_ref.py) on CPU.
+Bar (BASELINE.json north_star): 1e-3 max-abs on fp32 pixels in the default fp16x3 mode."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from impersonator_b200 import synthetic as S
+from impersonator_b200.generator import ImpersonatorGenerator
+from oracle import generator_ref as G
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3
+
+
+def sl(t):
+    return t[:, :, 3::8, 5::8].cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def net(cuda):
+    torch.set_grad_enabled(False)
+    n = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    sd = S.fill_state_dict(n.state_dict(), seed=0)
+    n.load_state_dict(sd)
+    return n.to(cuda).eval(), sd
+
+
+def test_inference_matches_reference_golden_and_oracle(cuda, net):
+    """encode_src + inference (networks/generator.py:213-214, 277-301), B=2 targets, 1 source."""
+    n, sd = net
+    g = np.load(os.path.join(GOLD, "generator.npz"))
+    inp = S.synthetic_generator_inputs(2, 256, seed=21)
+    enc, res = n.encode_src(inp["src"].to(cuda))
+    img, mask = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda))
+    torch.cuda.synchronize()
+    d_img = np.abs(sl(img) - g["inf_tsf_img"]).max()
+    d_mask = np.abs(sl(mask) - g["inf_tsf_mask"]).max()
+    d_enc = np.abs(enc[3][:, ::16, ::4, ::4].cpu().numpy() - g["inf_enc3"]).max()
+    d_res = np.abs(res[5][:, ::16, ::4, ::4].cpu().numpy() - g["inf_res5"]).max()
+    print("vs reference golden: tsf_img %.3e tsf_mask %.3e enc3 %.3e res5 %.3e" % (d_img, d_mask, d_enc, d_res))
+    assert d_img < TOL and d_mask < TOL and d_enc < TOL and d_res < 5 * TOL
+    e_o, r_o = G.encode_src(inp["src"], sd)
+    img_o, mask_o = G.inference(e_o, r_o, inp["tsf"], inp["T"], sd)
+    f_img = (img.cpu() - img_o).abs().max().item()
+    f_mask = (mask.cpu() - mask_o).abs().max().item()
+    print("vs oracle full tensors: tsf_img %.3e tsf_mask %.3e" % (f_img, f_mask))
+    assert f_img < TOL and f_mask < TOL
+    bg = torch.rand(1, 3, 256, 256) * 2 - 1
+    _, _, pred = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda), bg=bg.to(cuda))
+    ref_pred = mask_o * bg + (1 - mask_o) * img_o                          # models/imitator.py:331
+    assert (pred.cpu() - ref_pred).abs().max().item() < TOL
+
+
+def test_forward_matches_reference_golden(cuda, net):
+    """Full ImpersonatorGenerator.forward (bg + src + tsf streams), BASELINE config 1."""
+    n, sd = net
+    g = np.load(os.path.join(GOLD, "generator.npz"))
+    inp = S.synthetic_generator_inputs(1, 256, seed=11)
+    outs = n(inp["bg"].to(cuda), inp["src"].to(cuda), inp["tsf"].to(cuda), inp["T"].to(cuda))
+    torch.cuda.synchronize()
+    for name, t in zip(("img_bg", "src_img", "src_mask", "tsf_img", "tsf_mask"), outs):
+        d = np.abs(sl(t) - g["fwd_" + name]).max()
+        print("forward %-9s vs reference golden: %.3e" % (name, d))
+        assert d < TOL
+
+
+def test_fast_mode_reports_its_error(cuda, net, monkeypatch):
+    """Single-pass fp16 ("fast") mode: measured, not parity-gated."""
+    n, sd = net
+    monkeypatch.setenv("LWB_PRECISION", "fp16")
+    g = np.load(os.path.join(GOLD, "generator.npz"))
+    inp = S.synthetic_generator_inputs(2, 256, seed=21)
+    enc, res = n.encode_src(inp["src"].to(cuda))
+    img, mask = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda))
+    d_img = np.abs(sl(img) - g["inf_tsf_img"]).max()
+    d_mask = np.abs(sl(mask) - g["inf_tsf_mask"]).max()
+    print("fast mode vs reference golden: tsf_img %.3e tsf_mask %.3e" % (d_img, d_mask))
+    assert d_img < 5e-2 and d_mask < 5e-2
+
+
+def test_swap_matches_oracle(cuda, net):
+    """ImpersonatorGenerator.swap (two LWB warps per site, networks/generator.py:245-275)."""
+    n, sd = net
+    a = S.synthetic_generator_inputs(1, 256, seed=31)
+    b = S.synthetic_generator_inputs(1, 256, seed=41)
+    e12, r12 = n.encode_src(a["src"].to(cuda))
+    e21, r21 = n.encode_src(b["src"].to(cuda))
+    img, mask = n.swap(a["tsf"].to(cuda), e12, e21, r12, r21, a["T"].to(cuda), b["T"].to(cuda))
+    eo12, ro12 = G.encode_src(a["src"], sd)
+    eo21, ro21 = G.encode_src(b["src"], sd)
+    img_o, mask_o = G.swap(a["tsf"], eo12, eo21, ro12, ro21, a["T"], b["T"], sd)
+    d1, d2 = (img.cpu() - img_o).abs().max().item(), (mask.cpu() - mask_o).abs().max().item()
+    print("swap vs oracle: %.3e %.3e" % (d1, d2))
+    assert d1 < TOL and d2 < TOL
