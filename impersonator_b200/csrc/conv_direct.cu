@@ -13,12 +13,15 @@ namespace {
 // Per (ky, c-chunk): 10 input float4 pairs feed 4 px x 7 kx x 8 c x 4 co = 896 FMAs.
 // ------------------------------------------------------------------------------------------
 constexpr int HT_H = 16, HT_W = 32, HC = 8, HALO = 3;
-constexpr int HP_H = HT_H + 2 * HALO, HP_W = HT_W + 2 * HALO;       // 22 x 38
+constexpr int HP_H = HT_H + 2 * HALO, HP_W = HT_W + 2 * HALO;       // 22 x 38 halo tile
+constexpr int HP_WP = 40;                                           // padded row pitch (floats), 16B aligned
 
 __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, const float* __restrict__ w4,
                                                   int n, int h, int w, float* __restrict__ out)
 {
-    __shared__ __align__(16) float s_in[HP_H][HP_W][HC];            // 26752 B
+    // s_in[row][channel][x]: a thread's 10 consecutive x of one channel are 3 aligned float4 loads and
+    // the 8 threads of a quarter-warp read 128 contiguous bytes -> no bank conflicts.
+    __shared__ __align__(16) float s_in[HP_H][HC][HP_WP];           // 28160 B
     __shared__ __align__(16) float s_w[49][HC][4];                  //  6272 B
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * HT_H, x0 = blockIdx.x * HT_W;
@@ -31,13 +34,16 @@ __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, c
 
     for (int c0 = 0; c0 < 64; c0 += HC) {
         __syncthreads();
-        for (int i = threadIdx.x; i < HP_H * HP_W * 2; i += 128) {
-            const int half = i & 1, px = (i >> 1) % HP_W, py = (i >> 1) / HP_W;
+        // fill: consecutive threads take consecutive x of one (row, channel-quad) -> coalesced 16B global
+        // reads (stride 256B between pixels) and conflict-free scalar smem stores
+        for (int i = threadIdx.x; i < HP_H * 2 * HP_WP; i += 128) {
+            const int px = i % HP_WP, half = (i / HP_WP) & 1, py = i / (2 * HP_WP);
             const int yy = y0 + py - HALO, xx = x0 + px - HALO;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+            if (px < HP_W && yy >= 0 && yy < h && xx >= 0 && xx < w)
                 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * h + yy) * w + xx) * 64 + c0) + half);
-            *reinterpret_cast<float4*>(&s_in[py][px][half * 4]) = v;
+            s_in[py][half * 4 + 0][px] = v.x; s_in[py][half * 4 + 1][px] = v.y;
+            s_in[py][half * 4 + 2][px] = v.z; s_in[py][half * 4 + 3][px] = v.w;
         }
         for (int i = threadIdx.x; i < 49 * HC; i += 128) {
             const int tap = i / HC, c = i % HC;
@@ -46,22 +52,21 @@ __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, c
         __syncthreads();
 #pragma unroll 1
         for (int ky = 0; ky < 7; ky++) {
-            float in[10][HC];
 #pragma unroll
-            for (int j = 0; j < 10; j++) {
-                const float4 a = *reinterpret_cast<const float4*>(&s_in[ty + ky][tx * 4 + j][0]);
-                const float4 c = *reinterpret_cast<const float4*>(&s_in[ty + ky][tx * 4 + j][4]);
-                in[j][0] = a.x; in[j][1] = a.y; in[j][2] = a.z; in[j][3] = a.w;
-                in[j][4] = c.x; in[j][5] = c.y; in[j][6] = c.z; in[j][7] = c.w;
-            }
+            for (int c = 0; c < HC; c++) {
+                float in[12];
+                const float4* src = reinterpret_cast<const float4*>(&s_in[ty + ky][c][tx * 4]);
 #pragma unroll
-            for (int kx = 0; kx < 7; kx++) {
+                for (int j = 0; j < 3; j++) {
+                    const float4 a = src[j];
+                    in[4 * j] = a.x; in[4 * j + 1] = a.y; in[4 * j + 2] = a.z; in[4 * j + 3] = a.w;
+                }
 #pragma unroll
-                for (int c = 0; c < HC; c++) {
+                for (int kx = 0; kx < 7; kx++) {
                     const float4 wv = *reinterpret_cast<const float4*>(&s_w[ky * 7 + kx][c][0]);
 #pragma unroll
                     for (int p = 0; p < 4; p++) {
-                        const float v = in[p + kx][c];
+                        const float v = in[p + kx];
                         acc[p][0] = fmaf(v, wv.x, acc[p][0]);
                         acc[p][1] = fmaf(v, wv.y, acc[p][1]);
                         acc[p][2] = fmaf(v, wv.z, acc[p][2]);

@@ -251,7 +251,39 @@ __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ raw, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// gated conv epilogue of the inpaintor (networks/inpaintor.py:37-47), NCHW fp32:
+//   ab = [conv2d(x) ; mask_conv2d(x)] stacked on channels;  y = act(a) * sigmoid(b);  out = y*scale + shift
+//   (scale/shift = eval-mode BatchNorm2d folded: gamma/sqrt(var+eps), beta - mean*scale)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gated_bn(const float* __restrict__ ab, int n, int c, int hw, int act,
+                                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                                  float* __restrict__ out)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n * c * hw) return;
+    const int p = (int)(i % hw), ch = (int)((i / hw) % c), b = (int)(i / ((long)hw * c));
+    float a = ab[((size_t)b * 2 * c + ch) * hw + p];
+    const float g = ab[((size_t)b * 2 * c + c + ch) * hw + p];
+    if (act == 2) a = a > 0.f ? a : 0.2f * a;
+    else if (act == 1) a = fmaxf(a, 0.f);
+    float y = a * (1.f / (1.f + expf(-g)));
+    if (scale) y = fmaf(y, __ldg(scale + ch), __ldg(shift + ch));
+    out[i] = y;
+}
+
 }  // namespace
+
+extern "C" int lwb_gated_bn_nchw(const float* ab, int n, int c, int h, int w, int act,
+                                 const float* scale, const float* shift, float* out, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(ab && out, "null pointer");
+    LWB_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0, "bad sizes");
+    LWB_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+    k_gated_bn<<<lwb::ceil_div((long)n * c * h * w, 256), 256, 0, (cudaStream_t)stream>>>(ab, n, c, h * w, act, scale, shift, out);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
 
 extern "C" int lwb_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int transposed,
                                     int cout_pad, int cin_pad, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream)

@@ -28,7 +28,8 @@
 namespace {
 
 constexpr int   kSmallBox   = 48;       // boxes up to this many pixels are walked by one thread
-constexpr float kSliverTol  = 1e-5f;    // |det| / (longest edge)^2 below this -> whole-image scan
+constexpr float kSliverTol  = 1e-5f;
+constexpr float kBoxMargin  = 0.02f;    // pixels added around the exact bounding box    // |det| / (longest edge)^2 below this -> whole-image scan
 
 struct RasterParams {
     // geometry source: either faces [B,F,3,3] or (cam, verts, face_idx)
@@ -103,8 +104,12 @@ __device__ __forceinline__ void face_setup(const float* f, int is, float* p, flo
     for (int k = 0; k < 9; k++) inv[k] = __fdiv_rn(a[k], det);
 }
 
-// rasterize_cuda_kernel.cu:113-114
-__device__ __forceinline__ float ndc_center(int i, int is) { return (float)((2. * i + 1 - is) / is); }
+// rasterize_cuda_kernel.cu:113-114: (float)((2.*i + 1 - is) / is), a double division rounded to float.
+// Numerator and denominator are integers < 2^24, i.e. exact floats, and for such operands a
+// correctly rounded double quotient rounded again to float equals the correctly rounded float
+// quotient (53 >= 2*24 + 2), so one IEEE fp32 division reproduces it bit for bit -- without the
+// two FP64 divisions per pixel test.
+__device__ __forceinline__ float ndc_center(int i, int is) { return __fdiv_rn((float)(2 * i + 1 - is), (float)is); }
 
 // rasterize_cuda_kernel.cu:132-134 (strict '<' rejects: a centre exactly on an edge is inside)
 __device__ __forceinline__ bool inside(const float* f, float xp, float yp)
@@ -193,9 +198,11 @@ __global__ void __launch_bounds__(256) k_face_raster(RasterParams P)
                 bx0 = 0; by0 = 0; bx1 = P.is - 1; by1 = P.is - 1;
                 mode = 2;
             } else {
-                // conservative box: one extra pixel on every side absorbs rounding of the edge tests
-                bx0 = max(0, (int)floorf(xmin) - 1); bx1 = min(P.is - 1, (int)ceilf(xmax) + 1);
-                by0 = max(0, (int)floorf(ymin) - 1); by1 = min(P.is - 1, (int)ceilf(ymax) + 1);
+                // Conservative box in pixel-centre coordinates (pixel i has p-coordinate exactly i).  For a
+                // non-sliver triangle a rounding-induced false accept of the reference's edge tests lies
+                // within ~1e-6 NDC (< 1e-3 px up to 2048^2) of the triangle; kBoxMargin absorbs that.
+                bx0 = max(0, (int)ceilf(xmin - kBoxMargin)); bx1 = min(P.is - 1, (int)floorf(xmax + kBoxMargin));
+                by0 = max(0, (int)ceilf(ymin - kBoxMargin)); by1 = min(P.is - 1, (int)floorf(ymax + kBoxMargin));
                 if (bx0 <= bx1 && by0 <= by1)
                     mode = ((bx1 - bx0 + 1) * (by1 - by0 + 1) <= kSmallBox) ? 1 : 2;
             }

@@ -365,6 +365,7 @@ def profile_streams(warm_fn, run_fn):
     for cls in ("conv", "norm", "heads", "correspond", "input"):
         r = raw.get(cls, {"ms": 0.0, "work": 0.0, "n": 0})
         out[cls] = {"ms": r["ms"], "n": r["n"], ("flops" if cls in ("conv", "heads") else "bytes"): r["work"]}
+    out["layers"] = {k: {"ms": v["ms"] / n, "n": v["n"] / n, "work": v["work"] / n} for k, v in raw.items() if "/" in k}
     return out
 
 

@@ -39,8 +39,8 @@ def _count(n):
 class _Prof(object):
     """with _Prof('conv', flops): ... -> CUDA events on the launching stream when profiling is on."""
 
-    def __init__(self, cls, work=0.0):
-        self.cls, self.work = cls, work
+    def __init__(self, cls, work=0.0, label=None):
+        self.cls, self.work, self.label = cls, work, label
 
     def __enter__(self):
         if _profile is not None:
@@ -53,6 +53,8 @@ class _Prof(object):
         if _profile is not None:
             self.e1.record()
             _profile.setdefault(self.cls, []).append((self.e0, self.e1, self.work))
+            if self.label:
+                _profile.setdefault(self.cls + "/" + self.label, []).append((self.e0, self.e1, self.work))
         return False
 
 
@@ -220,6 +222,8 @@ class ConvPlan(object):
         self._h = handle
         self.num_launches = lib().lwb_conv_plan_num_launches(handle)
         d = desc
+        self.label = "%s%dx%ds%d %d->%d @%d" % ("T" if d.transposed else ("R" if d.rowk else "C"), d.kh, d.kw, d.stride,
+                                                d.cin0 + d.cin1, d.cout, d.h_out)
         if d.transposed:       # algorithmic 2*MAC: every input pixel meets every (tap, cin, cout)
             self.flops = 2.0 * d.n * d.h_in * d.w_in * d.cin0 * d.cout * d.kh * d.kw
         elif d.rowk:
@@ -229,7 +233,7 @@ class ConvPlan(object):
 
     def run(self):
         _count(self.num_launches)
-        with _Prof("conv", self.flops):
+        with _Prof("conv", self.flops, self.label):
             check(lib().lwb_conv_plan_run(self._h, stream()), "lwb_conv_plan_run")
 
     def __del__(self):
@@ -277,7 +281,7 @@ def norm_act_nhwc(raw, stats, gamma, beta, relu, ws, eps=1e-5, residual=None, wa
     per = 4 + (4 if residual is not None else 0) + (4 if y_f32 is not None else 0) \
         + (2 if y_hi is not None else 0) + (2 if y_lo is not None else 0)
     nbytes = n * h * w * c * per + (warp_src.numel() * 4 + n * h * w * 8 if warp_src is not None else 0)
-    with _Prof("norm", nbytes):
+    with _Prof("norm", nbytes, "%dx%d c%d%s%s" % (h, w, c, " +res" if residual is not None else "", " +warp" if warp_src is not None else "")):
         check(lib().lwb_norm_act_nhwc(ptr(raw), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if relu else 0, n, h, w, c,
                                       ptr(residual), ptr(warp_src), sb, ptr(T), th, tw, 1 if align_corners else 0,
                                       ptr(ws), ptr(y_f32), ptr(y_hi), ptr(y_lo), stream()), "lwb_norm_act_nhwc")
@@ -330,4 +334,14 @@ def conv2d_direct_nchw(x, w, bias=None, stride=1, pad=0, dil=1):
     out = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
     check(lib().lwb_conv2d_direct_nchw(ptr(x), ptr(w), ptr(bias), n, cin, h, wd, cout, kh, kw, stride, pad, dil,
                                        ptr(out), stream()), "lwb_conv2d_direct_nchw")
+    return out
+
+
+def gated_bn_nchw(ab, act, scale=None, shift=None):
+    """networks/inpaintor.py:37-47: act(a)*sigmoid(b) followed by folded eval-mode BatchNorm."""
+    _chk_cuda(ab, scale, shift)
+    n, c2, h, w = ab.shape
+    out = torch.empty((n, c2 // 2, h, w), dtype=torch.float32, device=ab.device)
+    check(lib().lwb_gated_bn_nchw(ptr(ab), n, c2 // 2, h, w, act, ptr(scale), ptr(shift), ptr(out), stream()),
+          "lwb_gated_bn_nchw")
     return out

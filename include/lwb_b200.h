@@ -185,6 +185,12 @@ int lwb_conv2d_direct_nchw(const float* x, const float* w, const float* bias,
                            int n, int cin, int h, int wd, int cout, int kh, int kw,
                            int stride, int pad, int dil, float* out, lwb_stream_t stream);
 
+/* Gated-conv epilogue of the inpaintor (networks/inpaintor.py:37-47): ab [n,2c,h,w] = conv2d(x) and
+ * mask_conv2d(x) stacked on channels; out [n,c,h,w] = (act(a) * sigmoid(b)) * scale[c] + shift[c]
+ * (eval-mode BatchNorm2d folded; scale/shift nullable).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.2). */
+int lwb_gated_bn_nchw(const float* ab, int n, int c, int h, int w, int act,
+                      const float* scale, const float* shift, float* out, lwb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
