@@ -24,7 +24,7 @@ class ConvDesc(ctypes.Structure):
     """struct lwb_conv_desc (include/lwb_b200.h)."""
     _fields_ = [(n, ctypes.c_int) for n in (
         "n", "h_in", "w_in", "h_out", "w_out", "cin0", "cin1", "cout",
-        "kh", "kw", "stride", "pad", "dil", "transposed", "split", "rowk", "row_pitch", "n_tile")]
+        "kh", "kw", "stride", "pad", "dil", "transposed", "split", "rowk", "row_pitch", "n_tile", "halo")]
 
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
@@ -34,7 +34,7 @@ SIGNATURES = {
     "lwb_version": (_i, []),
     "lwb_last_error": (ctypes.c_char_p, []),
     "lwb_device_info": (_i, [_vp, _vp, _vp]),
-    "lwb_raster_workspace_bytes": (_sz, [_i, _i]),
+    "lwb_raster_workspace_bytes": (_sz, [_i, _i, _i]),
     "lwb_raster_forward_face_index_map": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "lwb_correspond": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _i, _vp, _vp, _i, _i,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

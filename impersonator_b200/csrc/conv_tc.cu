@@ -170,6 +170,68 @@ __device__ __forceinline__ float warp_col_sums(float* v, unsigned lane) {
     return v[0];
 }
 
+
+// Epilogue warps (4): TMEM accumulator -> fp32 NHWC global + InstanceNorm partial statistics.
+template <int N_TILE, class PT>
+__device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned lane, int total_tiles, int m_tiles,
+                                              uint32_t tmem_base, uint64_t* bar_tfull, uint64_t* bar_tempty, float2* s_stats)
+{
+    const int q = warp & 3;                                     // TMEM lane quarter this warp may access
+    const int row = q * 32 + (int)lane;
+    const int ty = row >> 3, tx = row & 7;
+    const int et = threadIdx.x - 64;                            // 0..127
+    int abuf = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile / m_tiles, m_idx = tile % m_tiles;
+        const int img = m_idx / (P.tiles_y * P.tiles_x);
+        const int rem = m_idx % (P.tiles_y * P.tiles_x);
+        const int y = (rem / P.tiles_x) * TILE_H + ty, x = (rem % P.tiles_x) * TILE_W + tx;
+        const bool valid = y < P.dom_h && x < P.dom_w;
+        float* optr = P.out + (((size_t)img * P.out_h + (P.oy_mul * y + P.oy_add)) * P.out_w + (P.ox_mul * x + P.ox_add)) * P.cout
+                    + (size_t)n_idx * N_TILE;
+        mbar_wait(bar_tfull + abuf, aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * N_TILE);
+        constexpr int CW = N_TILE >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c = 0; c < N_TILE / CW; c++) {
+            uint32_t r[CW];
+            if (CW == 32) tmem_ld32(taddr + c * CW, r); else tmem_ld16(taddr + c * CW, r);
+            tmem_ld_wait();
+            if (valid) {
+                float4* o = reinterpret_cast<float4*>(optr + c * CW);
+#pragma unroll
+                for (int j = 0; j < CW / 4; j++)
+                    o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            }
+            if (P.stats) {
+                float v[CW], v2[CW];
+#pragma unroll
+                for (int j = 0; j < CW; j++) { const float t = valid ? __uint_as_float(r[j]) : 0.f; v[j] = t; v2[j] = t * t; }
+                const float s1 = warp_col_sums<CW>(v, lane);
+                const float s2 = warp_col_sums<CW>(v2, lane);
+                if ((int)lane < CW) s_stats[q * N_TILE + c * CW + lane] = make_float2(s1, s2);
+            }
+        }
+        // all TMEM reads of this buffer are complete: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + abuf);
+        if (P.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int col = et; col < N_TILE; col += 128) {
+                const float2 a = s_stats[col], b = s_stats[N_TILE + col], cc = s_stats[2 * N_TILE + col], d = s_stats[3 * N_TILE + col];
+                double* dst = P.stats + 2 * ((size_t)img * P.cout + (size_t)n_idx * N_TILE + col);
+                atomicAdd(dst, (double)((a.x + b.x) + (cc.x + d.x)));
+                atomicAdd(dst + 1, (double)((a.y + b.y) + (cc.y + d.y)));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+    }
+}
+
 // ----------------------------------------------------------------------------------- kernel
 template <int N_TILE, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvParams P)
@@ -272,60 +334,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
         }
     } else {
         // ================================ epilogue (4 warps) ===========================
-        const int q = warp & 3;                                     // TMEM lane quarter this warp may access
-        const int row = q * 32 + (int)lane;
-        const int ty = row >> 3, tx = row & 7;
-        const int et = threadIdx.x - 64;                            // 0..127
-        int abuf = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int n_idx = tile / m_tiles, m_idx = tile % m_tiles;
-            const int img = m_idx / (P.tiles_y * P.tiles_x);
-            const int rem = m_idx % (P.tiles_y * P.tiles_x);
-            const int y = (rem / P.tiles_x) * TILE_H + ty, x = (rem % P.tiles_x) * TILE_W + tx;
-            const bool valid = y < P.dom_h && x < P.dom_w;
-            float* optr = P.out + (((size_t)img * P.out_h + (P.oy_mul * y + P.oy_add)) * P.out_w + (P.ox_mul * x + P.ox_add)) * P.cout
-                        + (size_t)n_idx * N_TILE;
-            mbar_wait(bar_tfull + abuf, aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * N_TILE);
-            constexpr int CW = N_TILE >= 32 ? 32 : 16;
-#pragma unroll 1
-            for (int c = 0; c < N_TILE / CW; c++) {
-                uint32_t r[CW];
-                if (CW == 32) tmem_ld32(taddr + c * CW, r); else tmem_ld16(taddr + c * CW, r);
-                tmem_ld_wait();
-                if (valid) {
-                    float4* o = reinterpret_cast<float4*>(optr + c * CW);
-#pragma unroll
-                    for (int j = 0; j < CW / 4; j++)
-                        o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                }
-                if (P.stats) {
-                    float v[CW], v2[CW];
-#pragma unroll
-                    for (int j = 0; j < CW; j++) { const float t = valid ? __uint_as_float(r[j]) : 0.f; v[j] = t; v2[j] = t * t; }
-                    const float s1 = warp_col_sums<CW>(v, lane);
-                    const float s2 = warp_col_sums<CW>(v2, lane);
-                    if ((int)lane < CW) s_stats[q * N_TILE + c * CW + lane] = make_float2(s1, s2);
-                }
-            }
-            // all TMEM reads of this buffer are complete: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + abuf);
-            if (P.stats) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int col = et; col < N_TILE; col += 128) {
-                    const float2 a = s_stats[col], b = s_stats[N_TILE + col], cc = s_stats[2 * N_TILE + col], d = s_stats[3 * N_TILE + col];
-                    double* dst = P.stats + 2 * ((size_t)img * P.cout + (size_t)n_idx * N_TILE + col);
-                    atomicAdd(dst, (double)((a.x + b.x) + (cc.x + d.x)));
-                    atomicAdd(dst + 1, (double)((a.y + b.y) + (cc.y + d.y)));
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-            if (++abuf == 2) { abuf = 0; aphase ^= 1; }
-        }
+        epilogue_loop<N_TILE>(P, warp, lane, total_tiles, m_tiles, tmem_base, bar_tfull, bar_tempty, s_stats);
     }
 
     tc_fence_before();
@@ -333,6 +342,180 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     tc_fence_after();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================
+// Halo variant (stride-1 k x k convs, and the row-K stem): the activation tile is fetched ONCE per
+// 64-channel chunk together with its halo -- (16 + kh - 1) rows of 16 pixels (8 + kw - 1 <= 16) -- and
+// every filter tap reads a shifted window of that one shared-memory tile through the UMMA descriptor:
+//   start address = tile + ky * pitch + kx * 128 B,  8-row-group stride (SBO) = pitch = 16 px * 128 B,
+//   descriptor base_offset = kx  (the 128B-swizzle phase of the first row, since the window no longer
+//   starts on a 1024 B boundary: phase = (address >> 7) & 7).
+// Activation traffic L2->SMEM drops from taps x 16 KB to (16+kh-1) x 2 KB per chunk (3x3: 4x less,
+// 7x7: 17x less); weights stream per (chunk, tap) through their own ring.  This is what makes the
+// narrow layers (Cout = 64 at 256^2, the 7x7 heads) tensor-bound instead of L2-bound.
+// =====================================================================================================
+struct HaloParams {
+    CUtensorMap a_hi[2];
+    CUtensorMap a_lo[2];
+    CUtensorMap w_hi;
+    CUtensorMap w_lo;
+    int n_img, tiles_y, tiles_x, n_tiles_n;
+    int dom_h, dom_w;
+    int kh, kw;                       // taps = kh * kw (row-K: kw = 1, the filter row lives in K)
+    int chunks0, chunks1;
+    int x_off, y_off;                 // halo box origin relative to the tile origin (-pad, or 0 for row-K)
+    int a_rows;                       // TILE_H + kh - 1
+    int pitch_bytes;                  // smem bytes per halo row: 2048 (16 px), or 1024 for row-K (8 positions)
+    int a_plane_bytes;                // a_rows * pitch_bytes (one of hi / lo)
+    int a_stage_bytes;                // a_plane_bytes * (SPLIT ? 2 : 1)
+    int nb_stages;
+    float* out; int out_h, out_w, cout;
+    int oy_mul, oy_add, ox_mul, ox_add;
+    double* stats;
+};
+
+constexpr int HALO_NA = 2;            // activation ring depth
+constexpr int HALO_MAX_NB = 8;        // weight ring depth (max)
+
+__device__ __forceinline__ uint64_t make_desc_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46)
+         | ((uint64_t)(base_offset & 7) << 49) | (2ull << 61);
+}
+
+template <int N_TILE, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_constant__ HaloParams P)
+{
+    constexpr int B_BYTES = N_TILE * 128;
+    constexpr int B_STAGE = B_BYTES * (SPLIT ? 2 : 1);
+    constexpr int TMEM_COLS = Cfg<N_TILE, SPLIT>::TMEM_COLS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + HALO_NA * P.a_stage_bytes;
+    uint8_t* tail = b_ring + P.nb_stages * B_STAGE;
+    uint64_t* bar_afull = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* bar_aempty = bar_afull + HALO_NA;
+    uint64_t* bar_bfull = bar_aempty + HALO_NA;
+    uint64_t* bar_bempty = bar_bfull + HALO_MAX_NB;
+    uint64_t* bar_tfull = bar_bempty + HALO_MAX_NB;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    float2* s_stats = reinterpret_cast<float2*>(tail + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    const int nb = P.nb_stages;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < HALO_NA; s++) { mbar_init(bar_afull + s, 1); mbar_init(bar_aempty + s, 1); }
+            for (int s = 0; s < nb; s++) { mbar_init(bar_bfull + s, 1); mbar_init(bar_bempty + s, 1); }
+            for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + b, 1); mbar_init(bar_tempty + b, 4); }
+            fence_barrier_init();
+            fence_proxy_async();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nchunks = P.chunks0 + P.chunks1;
+    const int ntaps = P.kh * P.kw;
+    const int m_tiles = P.n_img * P.tiles_y * P.tiles_x;
+    const int total_tiles = m_tiles * P.n_tiles_n;
+
+    if (warp == 0) {
+        // ================================ TMA producer =================================
+        if (lane == 0) {
+            int sa = 0; uint32_t pa = 0;
+            int sb = 0; uint32_t pb = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_idx = tile / m_tiles, m_idx = tile % m_tiles;
+                const int img = m_idx / (P.tiles_y * P.tiles_x);
+                const int rem = m_idx % (P.tiles_y * P.tiles_x);
+                const int y0 = (rem / P.tiles_x) * TILE_H + P.y_off, x0 = (rem % P.tiles_x) * TILE_W + P.x_off;
+                for (int chunk = 0; chunk < nchunks; chunk++) {
+                    const bool second = chunk >= P.chunks0;
+                    const int mi = second ? 1 : 0;
+                    const int c0 = (second ? chunk - P.chunks0 : chunk) * KCHUNK;
+                    mbar_wait(bar_aempty + sa, pa ^ 1);
+                    uint8_t* sta = a_ring + sa * P.a_stage_bytes;
+                    mbar_expect_tx(bar_afull + sa, (uint32_t)P.a_stage_bytes);
+                    tma_load_4d(&P.a_hi[mi], sta, bar_afull + sa, c0, x0, y0, img);
+                    if (SPLIT) tma_load_4d(&P.a_lo[mi], sta + P.a_plane_bytes, bar_afull + sa, c0, x0, y0, img);
+                    if (++sa == HALO_NA) { sa = 0; pa ^= 1; }
+                    for (int tap = 0; tap < ntaps; tap++) {
+                        mbar_wait(bar_bempty + sb, pb ^ 1);
+                        uint8_t* stb = b_ring + sb * B_STAGE;
+                        mbar_expect_tx(bar_bfull + sb, (uint32_t)B_STAGE);
+                        tma_load_3d(&P.w_hi, stb, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
+                        if (SPLIT) tma_load_3d(&P.w_lo, stb + B_BYTES, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
+                        if (++sb == nb) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ===================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int sa = 0; uint32_t pa = 0;
+            int sb = 0; uint32_t pb = 0;
+            int abuf = 0; uint32_t aphase = 0;
+            const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(bar_tempty + abuf, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * N_TILE);
+                for (int chunk = 0; chunk < nchunks; chunk++) {
+                    mbar_wait(bar_afull + sa, pa);
+                    tc_fence_after();
+                    const uint32_t a_hi = a_ring_u + sa * P.a_stage_bytes;
+                    const uint32_t a_lo = a_hi + P.a_plane_bytes;
+                    for (int tap = 0; tap < ntaps; tap++) {
+                        mbar_wait(bar_bfull + sb, pb);
+                        tc_fence_after();
+                        const int ky = tap / P.kw, kx = tap - ky * P.kw;
+                        const uint32_t a_off = (uint32_t)(ky * P.pitch_bytes + kx * 128);
+                        const uint32_t b_hi = b_ring_u + sb * B_STAGE;
+                        const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+                        for (int k = 0; k < KCHUNK / 16; k++) {
+                            const uint64_t da = make_desc_ex(a_hi + a_off + k * 32, (uint32_t)P.pitch_bytes, (uint32_t)kx);
+                            const uint64_t db = make_desc(b_hi + k * 32);
+                            umma_f16(d_tmem, da, db, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                            if (SPLIT) {
+                                umma_f16(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
+                                umma_f16(d_tmem, make_desc_ex(a_lo + a_off + k * 32, (uint32_t)P.pitch_bytes, (uint32_t)kx), db, idesc, 1u);
+                            }
+                        }
+                        umma_commit(bar_bempty + sb);
+                        if (++sb == nb) { sb = 0; pb ^= 1; }
+                    }
+                    umma_commit(bar_aempty + sa);
+                    if (++sa == HALO_NA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(bar_tfull + abuf);
+                if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        epilogue_loop<N_TILE>(P, warp, lane, total_tiles, m_tiles, tmem_base, bar_tfull, bar_tempty, s_stats);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 
@@ -377,10 +560,26 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
 
 struct Launch {
     ConvParams p;
+    HaloParams h;
+    bool halo;
+    int halo_smem;
     int n_tile;
     bool split;
     int grid;
 };
+
+template <int N_TILE, bool SPLIT>
+int launch_halo_one(const Launch& L, cudaStream_t st)
+{
+    static int attr_smem = 0;
+    if (L.halo_smem > attr_smem) {
+        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_halo<N_TILE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.halo_smem));
+        attr_smem = L.halo_smem;
+    }
+    k_conv_halo<N_TILE, SPLIT><<<L.grid, NUM_THREADS, L.halo_smem, st>>>(L.h);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
 
 template <int N_TILE, bool SPLIT>
 int launch_one(const Launch& L, cudaStream_t st)
@@ -398,6 +597,16 @@ int launch_one(const Launch& L, cudaStream_t st)
 
 int launch(const Launch& L, cudaStream_t st)
 {
+    if (L.halo) {
+        switch (L.n_tile) {
+            case 16:  return L.split ? launch_halo_one<16, true>(L, st) : launch_halo_one<16, false>(L, st);
+            case 64:  return L.split ? launch_halo_one<64, true>(L, st) : launch_halo_one<64, false>(L, st);
+            case 128: return L.split ? launch_halo_one<128, true>(L, st) : launch_halo_one<128, false>(L, st);
+            case 256: return L.split ? launch_halo_one<256, true>(L, st) : launch_halo_one<256, false>(L, st);
+        }
+        lwb::set_error("conv_halo: unsupported N tile %d", L.n_tile);
+        return LWB_E_UNSUPPORTED;
+    }
     switch (L.n_tile) {
         case 16:  return L.split ? launch_one<16, true>(L, st) : launch_one<16, false>(L, st);
         case 64:  return L.split ? launch_one<64, true>(L, st) : launch_one<64, false>(L, st);
@@ -471,10 +680,81 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.n_tiles_n = d->cout / n_tile;
         p.out = out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
-        L.n_tile = n_tile; L.split = split;
+        L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0;
         const long total = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
         L.grid = (int)(total < sms ? total : sms);
     };
+
+    if (d->halo) {
+        // Halo variant: stride-1 k x k conv (pad = k/2, dil 1, optional concat input) or the row-K stem.
+        LWB_CHECK_ARG(d->stride == 1 && !d->transposed && d->dil == 1, "halo mode needs stride 1, dilation 1, not transposed");
+        Launch& L = plan->launches[plan->num++];
+        memset(&L.h, 0, sizeof(L.h));
+        HaloParams& h = L.h;
+        L.halo = true;
+        const int b_stage = n_tile * 128 * (split ? 2 : 1);
+        if (d->rowk) {
+            LWB_CHECK_ARG(d->kw <= 8 && d->cin0 == 8 && d->cin1 == 0 && d->row_pitch >= d->w_in + 8, "row-K shape");
+            const int hp = d->h_in + d->kh - 1;
+            h.kh = d->kh; h.kw = 1; h.x_off = 0; h.y_off = 0;
+            h.a_rows = TILE_H + d->kh - 1; h.pitch_bytes = TILE_W * 128;
+            const uint64_t dims[4] = {64, (uint64_t)d->w_in, (uint64_t)hp, (uint64_t)d->n};
+            const uint64_t str[3] = {16, (uint64_t)d->row_pitch * 16, (uint64_t)hp * d->row_pitch * 16};
+            const uint32_t box[4] = {KCHUNK, TILE_W, (uint32_t)h.a_rows, 1};
+            if ((rc = encode_map(&h.a_hi[0], x0_hi, 4, dims, str, box)) != LWB_OK) return fail(rc);
+            if (split && (rc = encode_map(&h.a_lo[0], x0_lo, 4, dims, str, box)) != LWB_OK) return fail(rc);
+            const uint64_t wd[3] = {64, (uint64_t)d->cout, (uint64_t)d->kh};
+            const uint64_t ws[2] = {128, (uint64_t)d->cout * 128};
+            const uint32_t wb[3] = {KCHUNK, (uint32_t)n_tile, 1};
+            if ((rc = encode_map(&h.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+            if (split && (rc = encode_map(&h.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+            h.chunks0 = 1; h.chunks1 = 0;
+        } else {
+            LWB_CHECK_ARG(d->kw <= 9 && d->kh == d->kw && d->pad == d->kh / 2, "halo mode needs an odd square kernel <= 9 with 'same' padding");
+            LWB_CHECK_ARG(d->cin0 % KCHUNK == 0 && d->cin1 % KCHUNK == 0 && d->cin0 > 0, "input channels must be multiples of 64");
+            LWB_CHECK_ARG(d->cin1 == 0 || (x1_hi && (!split || x1_lo)), "second input missing");
+            h.kh = d->kh; h.kw = d->kw; h.x_off = -d->pad; h.y_off = -d->pad;
+            h.a_rows = TILE_H + d->kh - 1; h.pitch_bytes = 16 * 128;
+            auto amap = [&](CUtensorMap* m, const uint16_t* base, int c) {
+                const uint64_t dims[4] = {(uint64_t)c, (uint64_t)d->w_in, (uint64_t)d->h_in, (uint64_t)d->n};
+                const uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)d->w_in * c * 2, (uint64_t)d->h_in * d->w_in * c * 2};
+                const uint32_t box[4] = {KCHUNK, 16, (uint32_t)h.a_rows, 1};
+                return encode_map(m, base, 4, dims, str, box);
+            };
+            if ((rc = amap(&h.a_hi[0], x0_hi, d->cin0)) != LWB_OK) return fail(rc);
+            if (split && (rc = amap(&h.a_lo[0], x0_lo, d->cin0)) != LWB_OK) return fail(rc);
+            if (d->cin1) {
+                if ((rc = amap(&h.a_hi[1], x1_hi, d->cin1)) != LWB_OK) return fail(rc);
+                if (split && (rc = amap(&h.a_lo[1], x1_lo, d->cin1)) != LWB_OK) return fail(rc);
+            }
+            const int cin_total = d->cin0 + d->cin1;
+            const uint64_t wd[3] = {(uint64_t)cin_total, (uint64_t)d->cout, (uint64_t)(d->kh * d->kw)};
+            const uint64_t ws[2] = {(uint64_t)cin_total * 2, (uint64_t)d->cout * cin_total * 2};
+            const uint32_t wb[3] = {KCHUNK, (uint32_t)n_tile, 1};
+            if ((rc = encode_map(&h.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+            if (split && (rc = encode_map(&h.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
+            h.chunks0 = d->cin0 / KCHUNK; h.chunks1 = d->cin1 / KCHUNK;
+        }
+        h.a_plane_bytes = h.a_rows * h.pitch_bytes;
+        h.a_stage_bytes = h.a_plane_bytes * (split ? 2 : 1);
+        const int fixed = 1024 + HALO_NA * h.a_stage_bytes + 256 + 4 * n_tile * 8;
+        int nbs = (227 * 1024 - fixed) / b_stage;
+        if (nbs > HALO_MAX_NB) nbs = HALO_MAX_NB;
+        if (nbs < 2) { lwb::set_error("conv_halo: tile does not fit shared memory (n_tile %d, kh %d)", n_tile, d->kh); return fail(LWB_E_UNSUPPORTED); }
+        h.nb_stages = nbs;
+        L.halo_smem = fixed + nbs * b_stage;
+        h.n_img = d->n; h.dom_h = d->h_out; h.dom_w = d->w_out;
+        h.tiles_y = lwb::ceil_div(d->h_out, TILE_H); h.tiles_x = lwb::ceil_div(d->w_out, TILE_W);
+        h.n_tiles_n = d->cout / n_tile;
+        h.out = out_raw; h.out_h = d->h_out; h.out_w = d->w_out; h.cout = d->cout;
+        h.oy_mul = 1; h.ox_mul = 1; h.oy_add = 0; h.ox_add = 0;
+        h.stats = stats;
+        L.n_tile = n_tile; L.split = split;
+        const long total = (long)h.n_img * h.tiles_y * h.tiles_x * h.n_tiles_n;
+        L.grid = (int)(total < sms ? total : sms);
+        *plan_out = plan;
+        return LWB_OK;
+    }
 
     if (d->rowk) {
         // 7x7 stem through the row-K trick.  Input: padded NHWC8 buffer [n, h_in + kh - 1, wp, 8] whose

@@ -158,72 +158,114 @@ struct NormActParams {
     float* y_f32; __half* y_hi; __half* y_lo;
 };
 
+// Block = 256 threads = (256 / groups) pixels x groups channel-octets, two pixel rounds per thread so
+// that four 16B loads per operand are in flight before any math.  The bilinear taps of a pixel are
+// computed once (by one thread) and shared through smem instead of once per channel octet.
+struct TapRec { int o00, m; float w00, w01, w10, w11; };
+
+template <bool WARP>
 __global__ void __launch_bounds__(256) k_norm_act(NormActParams P)
 {
+    constexpr int R = 2;                                 // pixel rounds per thread
     const int groups = P.c >> 3;
-    const long total = (long)P.n * P.h * P.w * groups;
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int g = (int)(i % groups);
-    const long pixg = i / groups;                       // global pixel index (n,h,w)
+    const int ppb = 256 / groups;                        // pixels per block per round (groups <= 256)
+    const int g = threadIdx.x % groups, lp = threadIdx.x / groups;
+    const long npix = (long)P.n * P.h * P.w;
     const int hw = P.h * P.w;
-    const int b = (int)(pixg / hw), pix = (int)(pixg % hw);
-    const size_t off = (size_t)pixg * P.c + g * 8;
+    const long pix0 = (long)blockIdx.x * (ppb * R);
+    __shared__ TapRec s_tap[512];                      // ppb * R <= 512 (c = 8)
+    if (WARP) {
+        if (threadIdx.x < ppb * R) {
+            const long pg = pix0 + threadIdx.x;
+            TapRec t = {0, 0, 0.f, 0.f, 0.f, 0.f};
+            if (pg < npix) {
+                const int b = (int)(pg / hw), pix = (int)(pg % hw);
+                float gx, gy;
+                lwb::flow_at(P.T + (size_t)b * P.th * P.tw * 2, P.th, P.tw, P.h, P.w, pix / P.w, pix % P.w, gx, gy);
+                lwb::Taps tp;
+                lwb::make_taps(gx, gy, P.h, P.w, P.align_corners, tp);
+                t.o00 = tp.o00; t.m = tp.m; t.w00 = tp.w00; t.w01 = tp.w01; t.w10 = tp.w10; t.w11 = tp.w11;
+            }
+            s_tap[threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+    if (lp >= ppb) return;                               // (256 % groups != 0 never happens for c = 64..2048)
 
-    float v[8];
-    {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(P.raw + off));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(P.raw + off) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-    }
-    if (P.ss) {
-        const float2* ss = P.ss + (size_t)b * P.c + g * 8;
+    float v[R][8];
+    bool ok[R];
+    size_t off[R];
+    int bb[R];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const float2 s = __ldg(ss + k); v[k] = fmaf(v[k], s.x, s.y); }
+    for (int r = 0; r < R; r++) {
+        const long pg = pix0 + r * ppb + lp;
+        ok[r] = pg < npix;
+        bb[r] = ok[r] ? (int)(pg / hw) : 0;
+        off[r] = (size_t)(ok[r] ? pg : 0) * P.c + g * 8;
+        const float4* src = reinterpret_cast<const float4*>(P.raw + off[r]);
+        const float4 a = ok[r] ? __ldg(src) : make_float4(0, 0, 0, 0), c = ok[r] ? __ldg(src + 1) : make_float4(0, 0, 0, 0);
+        v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w; v[r][4] = c.x; v[r][5] = c.y; v[r][6] = c.z; v[r][7] = c.w;
     }
-    if (P.relu) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = fmaxf(v[k], 0.f);
-    }
+    float res[R][8];
     if (P.residual) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(P.residual + off));
-        const float4 c = __ldg(reinterpret_cast<const float4*>(P.residual + off) + 1);
-        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += c.x; v[5] += c.y; v[6] += c.z; v[7] += c.w;
-    }
-    if (P.warp_src) {
-        const int y = pix / P.w, x = pix % P.w;
-        float gx, gy;
-        lwb::flow_at(P.T + (size_t)b * P.th * P.tw * 2, P.th, P.tw, P.h, P.w, y, x, gx, gy);
-        lwb::Taps tp;
-        lwb::make_taps(gx, gy, P.h, P.w, P.align_corners, tp);
-        const float* src = P.warp_src + (size_t)(P.src_batch == 1 ? 0 : b) * hw * P.c + g * 8;
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const int offs[4] = {tp.o00, tp.o00 + 1, tp.o00 + P.w, tp.o00 + P.w + 1};
-        const float wt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            if (tp.m & (1 << t)) {
-                const float4* p = reinterpret_cast<const float4*>(src + (size_t)offs[t] * P.c);
-                const float4 a = __ldg(p), c = __ldg(p + 1);
-                acc[0] += a.x * wt[t]; acc[1] += a.y * wt[t]; acc[2] += a.z * wt[t]; acc[3] += a.w * wt[t];
-                acc[4] += c.x * wt[t]; acc[5] += c.y * wt[t]; acc[6] += c.z * wt[t]; acc[7] += c.w * wt[t];
+        for (int r = 0; r < R; r++) {
+            const float4* src = reinterpret_cast<const float4*>(P.residual + off[r]);
+            const float4 a = ok[r] ? __ldg(src) : make_float4(0, 0, 0, 0), c = ok[r] ? __ldg(src + 1) : make_float4(0, 0, 0, 0);
+            res[r][0] = a.x; res[r][1] = a.y; res[r][2] = a.z; res[r][3] = a.w; res[r][4] = c.x; res[r][5] = c.y; res[r][6] = c.z; res[r][7] = c.w;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (P.ss) {
+            const float4* ss = reinterpret_cast<const float4*>(P.ss + (size_t)bb[r] * P.c + g * 8);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 s2 = __ldg(ss + k);         // (scale, shift) of channels 2k, 2k+1
+                v[r][2 * k] = fmaf(v[r][2 * k], s2.x, s2.y);
+                v[r][2 * k + 1] = fmaf(v[r][2 * k + 1], s2.z, s2.w);
             }
         }
+        if (P.relu) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] += acc[k];
-    }
-    if (P.y_f32) {
-        float4* o = reinterpret_cast<float4*>(P.y_f32 + off);
-        o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    if (P.y_hi) {
-        __align__(16) __half hh[8];
-        __align__(16) __half ll[8];
+            for (int k = 0; k < 8; k++) v[r][k] = fmaxf(v[r][k], 0.f);
+        }
+        if (P.residual) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) split_half(v[k], hh[k], ll[k]);
-        *reinterpret_cast<uint4*>(P.y_hi + off) = *reinterpret_cast<const uint4*>(hh);
-        if (P.y_lo) *reinterpret_cast<uint4*>(P.y_lo + off) = *reinterpret_cast<const uint4*>(ll);
+            for (int k = 0; k < 8; k++) v[r][k] += res[r][k];
+        }
+        if (WARP) {
+            const TapRec tp = s_tap[r * ppb + lp];
+            const float* src = P.warp_src + (size_t)(P.src_batch == 1 ? 0 : bb[r]) * hw * P.c + g * 8;
+            const int offs[4] = {tp.o00, tp.o00 + 1, tp.o00 + P.w, tp.o00 + P.w + 1};
+            const float wt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                if (tp.m & (1 << t)) {
+                    const float4* q = reinterpret_cast<const float4*>(src + (size_t)offs[t] * P.c);
+                    const float4 a = __ldg(q), c = __ldg(q + 1);
+                    acc[0] += a.x * wt[t]; acc[1] += a.y * wt[t]; acc[2] += a.z * wt[t]; acc[3] += a.w * wt[t];
+                    acc[4] += c.x * wt[t]; acc[5] += c.y * wt[t]; acc[6] += c.z * wt[t]; acc[7] += c.w * wt[t];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[r][k] += acc[k];
+        }
+        if (!ok[r]) continue;
+        if (P.y_f32) {
+            float4* o = reinterpret_cast<float4*>(P.y_f32 + off[r]);
+            o[0] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+            o[1] = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+        }
+        if (P.y_hi) {
+            __align__(16) __half hh[8];
+            __align__(16) __half ll[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) split_half(v[r][k], hh[k], ll[k]);
+            *reinterpret_cast<uint4*>(P.y_hi + off[r]) = *reinterpret_cast<const uint4*>(hh);
+            if (P.y_lo) *reinterpret_cast<uint4*>(P.y_lo + off[r]) = *reinterpret_cast<const uint4*>(ll);
+        }
     }
 }
 
@@ -367,8 +409,11 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
     P.residual = residual;
     P.warp_src = warp_src; P.src_batch = src_batch; P.T = T; P.th = th; P.tw = tw; P.align_corners = align_corners;
     P.y_f32 = y_f32; P.y_hi = (__half*)y_hi; P.y_lo = (__half*)y_lo;
-    const long total = (long)n * h * w * (c / 8);
-    k_norm_act<<<lwb::ceil_div(total, 256), 256, 0, st>>>(P);
+    const int groups = c / 8;
+    LWB_CHECK_ARG(groups <= 256 && 256 % groups == 0, "channels / 8 must divide 256");
+    const long blocks = lwb::ceil_div((long)n * h * w, (256 / groups) * 2);
+    if (warp_src) k_norm_act<true><<<(unsigned)blocks, 256, 0, st>>>(P);
+    else          k_norm_act<false><<<(unsigned)blocks, 256, 0, st>>>(P);
     LWB_LAUNCH_OK();
     return LWB_OK;
 }

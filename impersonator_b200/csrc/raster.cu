@@ -40,6 +40,8 @@ struct RasterParams {
     int B, V, F, is;
     float nearv, farv, eye_z;
     unsigned long long* zbuf;           // [B,is,is] packed (depth bits << 32 | face)
+    unsigned* qcount;                   // deferred whole-image faces: counter (0xFFFFFFFF = empty) ...
+    unsigned* queue;                    // ... and entries (b * F + face), capacity B * F
     float* f2verts;                     // nullable [B,F,3,3]
     float* faces_inv;                   // nullable [B,F,3,3]
     // resolve outputs (raster API)
@@ -195,8 +197,10 @@ __global__ void __launch_bounds__(256) k_face_raster(RasterParams P)
             // exactly like the reference does.
             const bool whole = !finite || !(fabsf(det) > kSliverTol * ex * ex);
             if (whole) {
-                bx0 = 0; by0 = 0; bx1 = P.is - 1; by1 = P.is - 1;
-                mode = 2;
+                // deferred to k_face_whole, where the whole grid shares the 65k-pixel scan of each such face
+                // (one warp walking a full image would straggle for ~1 ms)
+                const unsigned slot = atomicAdd(P.qcount, 1u) + 1u;          // counter starts at 0xFFFFFFFF
+                P.queue[slot] = (unsigned)gid;
             } else {
                 // Conservative box in pixel-centre coordinates (pixel i has p-coordinate exactly i).  For a
                 // non-sliver triangle a rounding-induced false accept of the reference's edge tests lies
@@ -226,6 +230,25 @@ __global__ void __launch_bounds__(256) k_face_raster(RasterParams P)
         const int bw = gx1 - gx0 + 1, n = bw * (gy1 - gy0 + 1);
         for (int i = lane; i < n; i += 32)
             test_pixel(P, g, ginv, gb, gfn, gx0 + i % bw, gy0 + i / bw);
+    }
+}
+
+// Faces whose inside test is not confined to their bounding box (degenerate / sliver / non-finite):
+// the reference effectively tests them against every pixel, and so does this kernel -- spread over the
+// whole grid: blockIdx.y strides over the queued faces, blockIdx.x over pixel chunks.
+template <bool FROM_VERTS>
+__global__ void __launch_bounds__(256) k_face_whole(RasterParams P)
+{
+    const unsigned count = *P.qcount + 1u;
+    const int npix = P.is * P.is;
+    for (unsigned slot = blockIdx.y; slot < count; slot += gridDim.y) {
+        const unsigned gid = P.queue[slot];
+        const int b = (int)(gid / (unsigned)P.F), fn = (int)(gid % (unsigned)P.F);
+        float f[9], p[6], inv[9], det;
+        load_face<FROM_VERTS>(P, b, fn, f);
+        face_setup(f, P.is, p, inv, det);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x)
+            test_pixel(P, f, inv, b, fn, i % P.is, i / P.is);
     }
 }
 
@@ -311,11 +334,16 @@ __global__ void __launch_bounds__(256) k_resolve(RasterParams P)
 int run(RasterParams& P, bool from_verts, bool correspond, cudaStream_t st)
 {
     const size_t zbytes = (size_t)P.B * P.is * P.is * sizeof(unsigned long long);
-    LWB_CUDA_OK(cudaMemsetAsync(P.zbuf, 0xff, zbytes, st));
+    P.qcount = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(P.zbuf) + zbytes);
+    P.queue = P.qcount + 4;
+    LWB_CUDA_OK(cudaMemsetAsync(P.zbuf, 0xff, zbytes + 16, st));      // z-buffer "empty" + queue counter "empty"
     const long nfaces = (long)P.B * P.F, npix = (long)P.B * P.is * P.is;
     const int t = 256;
     if (from_verts) k_face_raster<true><<<lwb::ceil_div(nfaces, t), t, 0, st>>>(P);
     else            k_face_raster<false><<<lwb::ceil_div(nfaces, t), t, 0, st>>>(P);
+    LWB_LAUNCH_OK();
+    if (from_verts) k_face_whole<true><<<dim3(64, 64), t, 0, st>>>(P);
+    else            k_face_whole<false><<<dim3(64, 64), t, 0, st>>>(P);
     LWB_LAUNCH_OK();
     if (from_verts && correspond) k_resolve<true, true><<<lwb::ceil_div(npix, t), t, 0, st>>>(P);
     else if (!from_verts && !correspond) k_resolve<false, false><<<lwb::ceil_div(npix, t), t, 0, st>>>(P);
@@ -326,10 +354,11 @@ int run(RasterParams& P, bool from_verts, bool correspond, cudaStream_t st)
 
 }  // namespace
 
-extern "C" size_t lwb_raster_workspace_bytes(int batch, int image_size)
+extern "C" size_t lwb_raster_workspace_bytes(int batch, int image_size, int num_faces)
 {
-    if (batch <= 0 || image_size <= 0) return 0;
-    return (size_t)batch * image_size * image_size * sizeof(unsigned long long);
+    if (batch <= 0 || image_size <= 0 || num_faces <= 0) return 0;
+    // z-buffer + queue counter (16 B) + queue of deferred faces (worst case: every face)
+    return (size_t)batch * image_size * image_size * sizeof(unsigned long long) + 16 + (size_t)batch * num_faces * sizeof(unsigned);
 }
 
 extern "C" int lwb_raster_forward_face_index_map(

@@ -43,6 +43,13 @@ def _align_corners():
     return os.environ.get("LWB_ALIGN_CORNERS", "0") == "1"
 
 
+def _halo_mode():
+    """LWB_HALO: 'auto' (default) = halo variant of the conv kernel where it pays (row-K stem, the
+    skippers, the 7x7 heads on tensor cores); '0' = never (per-tap TMA loads, CUDA-core heads);
+    'all' = also the 512-channel residual blocks."""
+    return os.environ.get("LWB_HALO", "auto")
+
+
 class NetworkBase(nn.Module):
     """networks/networks.py:45-80."""
 
@@ -136,22 +143,24 @@ class _StreamBase(object):
             self._raw[key] = torch.empty((self.B, h, w, c), dtype=torch.float32, device=self.dev)
         return self._raw[key]
 
-    def _make_layer(self, conv, norm, x0, x1=None, stride=1, transposed=False, rowk=False, row_pitch=0, h=None, w=None):
+    def _make_layer(self, conv, norm, x0, x1=None, stride=1, transposed=False, rowk=False, row_pitch=0, h=None, w=None,
+                    halo=False, weight=None, pad=None, n_tile=0):
         L = _Layer()
-        wt = conv.weight.detach()
+        wt = (weight if weight is not None else conv.weight).detach()
         if rowk:
             L.w = K.pack_conv_weight_rowk(wt, split=self.split)
             cout, kh, kw = wt.shape[0], wt.shape[2], wt.shape[3]
             d = K.make_conv_desc(self.B, h, w, 8, cout, kh, kw, stride=1, pad=kh // 2, split=self.split,
-                                 rowk=True, row_pitch=row_pitch)
+                                 rowk=True, row_pitch=row_pitch, halo=halo)
         else:
             L.w = K.pack_conv_weight(wt, transposed=transposed, split=self.split)
             cout = wt.shape[1] if transposed else wt.shape[0]
             kh, kw = wt.shape[2], wt.shape[3]
             cin0 = x0[0].shape[3]
             cin1 = x1[0].shape[3] if x1 is not None else 0
-            d = K.make_conv_desc(self.B, h, w, cin0, cout, kh, kw, stride=stride, pad=conv.padding[0],
-                                 cin1=cin1, transposed=transposed, split=self.split)
+            d = K.make_conv_desc(self.B, h, w, cin0, cout, kh, kw, stride=stride,
+                                 pad=(pad if pad is not None else conv.padding[0]),
+                                 cin1=cin1, transposed=transposed, split=self.split, halo=halo, n_tile=n_tile)
         L.raw = self._raw_buf(d.h_out, d.w_out, cout)
         L.stats = (len(self._stats_slots), cout)
         self._stats_slots.append(cout)
@@ -162,13 +171,14 @@ class _StreamBase(object):
         return L
 
     def _finalize(self):
-        cmax = max(self._stats_slots)
+        cmax = max(max(self._stats_slots), 16)
         self.stats = torch.zeros((len(self._stats_slots), self.B, cmax, 2), dtype=torch.float64, device=self.dev)
         self.ws = torch.empty((self.B, cmax, 2), dtype=torch.float32, device=self.dev)
         for L in self._layers:
             slot, cout = L.stats
-            # per-layer contiguous [B, cout, 2] view at the head of the slot
-            L.stats = self.stats[slot].view(-1)[:self.B * cout * 2].view(self.B, cout, 2)
+            # per-layer contiguous [B, cout, 2] view at the head of the slot (None: no norm follows)
+            L.stats = None if self._stats_slots[slot] == 0 else \
+                self.stats[slot].view(-1)[:self.B * cout * 2].view(self.B, cout, 2)
             d, x0, x1 = L.plan
             L.plan = K.ConvPlan(d, x0, x1, L.w, L.raw, L.stats)
 
@@ -197,8 +207,9 @@ class _UnetStream(_StreamBase):
         # encoders
         self.e, self.enc_layers = [], []
         c, h, w = net.encoders[0][0].weight.shape[0], H, W
+        hm = _halo_mode()
         self.enc_layers.append(self._make_layer(net.encoders[0][0], net.encoders[0][1], self.x_pad.pair, rowk=True,
-                                                row_pitch=self.pitch, h=H, w=W))
+                                                row_pitch=self.pitch, h=H, w=W, halo=(hm != '0')))
         self.e.append(_Act((B, h, w, c), dev, split, want_f32=keep_f32))
         for i in range(1, nd + 1):
             self.enc_layers.append(self._make_layer(net.encoders[i][0], net.encoders[i][1], self.e[i - 1].pair,
@@ -211,8 +222,8 @@ class _UnetStream(_StreamBase):
         prev = self.e[nd]
         for i in range(self.repeat):
             out = _Act((B, h, w, c), dev, split, want_f32=True)
-            l1 = self._make_layer(net.resnets[i].main[0], net.resnets[i].main[1], prev.pair, h=h, w=w)
-            l2 = self._make_layer(net.resnets[i].main[3], net.resnets[i].main[4], self.hb.pair, h=h, w=w)
+            l1 = self._make_layer(net.resnets[i].main[0], net.resnets[i].main[1], prev.pair, h=h, w=w, halo=(hm == 'all'))
+            l2 = self._make_layer(net.resnets[i].main[3], net.resnets[i].main[4], self.hb.pair, h=h, w=w, halo=(hm == 'all'))
             self.res_layers.append((l1, l2))
             self.res_out.append(out)
             prev = out
@@ -223,14 +234,26 @@ class _UnetStream(_StreamBase):
             ld = self._make_layer(net.decoders[i][0], net.decoders[i][1], prev.pair, stride=2, transposed=True, h=h, w=w)
             c, h, w = c // 2, h * 2, w * 2
             last = (i == nd - 1)
-            out = _Act((B, h, w, c), dev, split, want_f32=last, want_half=not last)
-            ls = self._make_layer(net.skippers[i][0], net.skippers[i][1], self.e[nd - 1 - i].pair, x1=up.pair, h=h, w=w)
+            tc_heads = (hm != '0')
+            out = _Act((B, h, w, c), dev, split, want_f32=(last and not tc_heads), want_half=(not last or tc_heads))
+            ls = self._make_layer(net.skippers[i][0], net.skippers[i][1], self.e[nd - 1 - i].pair, x1=up.pair, h=h, w=w,
+                                  halo=(hm != '0'))
             self.dec_layers.append((ld, ls))
             self.d_up.append(up)
             self.d_out.append(out)
             prev = out
-        self.w4 = K.pack_head_weights(net.img_reg[0].weight.detach(), net.attetion_reg[0].weight.detach())
-        self.head_raw = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        w_img, w_att = net.img_reg[0].weight.detach(), net.attetion_reg[0].weight.detach()
+        self.head_layer = None
+        if hm != '0':
+            # img_reg (64->3) + attetion_reg (64->1) as one 7x7 conv padded to 16 output channels on the
+            # tensor cores (halo variant, N tile 16); channels 0..3 are consumed by the composite kernel
+            w16 = torch.cat([w_img, w_att, torch.zeros(12, *w_img.shape[1:], device=w_img.device, dtype=w_img.dtype)], dim=0)
+            self.head_layer = self._make_layer(None, None, prev.pair, h=H, w=W, halo=True, weight=w16, pad=3, n_tile=16)
+            self._stats_slots[-1] = 0          # no InstanceNorm after the heads: no statistics
+            self.head_raw = self.head_layer.raw
+        else:
+            self.w4 = K.pack_head_weights(w_img, w_att)
+            self.head_raw = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
         self._finalize()
 
     # ---- pieces -------------------------------------------------------------------------
@@ -275,7 +298,10 @@ class _UnetStream(_StreamBase):
             self._conv_norm(ls, self.d_out[i], True)
 
     def heads(self, bg=None, want_color=True, want_mask=True):
-        K.conv7x7_heads_nhwc(self.d_out[-1].f32, self.w4, out=self.head_raw)
+        if self.head_layer is not None:
+            self.head_layer.plan.run()
+        else:
+            K.conv7x7_heads_nhwc(self.d_out[-1].f32, self.w4, out=self.head_raw)
         return K.heads_composite(self.head_raw, bg, want_color=want_color, want_mask=want_mask)
 
     def encoder_outs_nchw(self):

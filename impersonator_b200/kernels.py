@@ -90,7 +90,7 @@ def raster_forward_face_index_map(faces, face_index_map, weight_map, depth_map, 
     if faces.dtype != torch.float32 or face_index_map.dtype != torch.int32 or weight_map.dtype != torch.float32:
         raise LwbError("faces/weight_map must be float32 and face_index_map int32")
     B, F = faces.shape[:2]
-    ws = _workspace(lib().lwb_raster_workspace_bytes(B, image_size), faces.device)
+    ws = _workspace(lib().lwb_raster_workspace_bytes(B, image_size, F), faces.device)
     check(lib().lwb_raster_forward_face_index_map(
         ptr(faces), B, F, image_size, near, far, ptr(face_index_map), ptr(weight_map), ptr(depth_map),
         ptr(faces_inv), 1 if flip_rows else 0, ptr(ws), stream()), "lwb_raster_forward_face_index_map")
@@ -121,8 +121,8 @@ def correspond(cam, verts, face_idx, image_size, map_fn, src_p2verts, src_img=No
                    T=torch.empty((B, s, s, 2), dtype=torch.float32, device=dev),
                    tsf_inputs=torch.empty((B, 3 + C, s, s), dtype=torch.float32, device=dev),
                    f2verts=torch.empty((B, F, 3, 3), dtype=torch.float32, device=dev) if want_f2verts else None)
-    ws = _workspace(lib().lwb_raster_workspace_bytes(B, s), dev)
-    _count(2)
+    ws = _workspace(lib().lwb_raster_workspace_bytes(B, s, F), dev)
+    _count(3)
     # algorithmic bytes: per frame verts + fim/wim/T/tsf_inputs; per batch the shared tables
     nbytes = B * (V * 12 + s * s * (4 + 12 + 8 + 4 * (3 + C))) + F * 12 + sb * F * 24 + (F + 1) * C * 4 + sb * 3 * s * s * 4
     with _Prof("correspond", nbytes):
@@ -246,7 +246,7 @@ class ConvPlan(object):
 
 
 def make_conv_desc(n, h_in, w_in, cin0, cout, kh, kw, stride=1, pad=0, dil=1, cin1=0, transposed=False,
-                   split=True, rowk=False, row_pitch=0, n_tile=0):
+                   split=True, rowk=False, row_pitch=0, n_tile=0, halo=False):
     if transposed:
         h_out, w_out = 2 * h_in, 2 * w_in
     elif rowk:
@@ -256,7 +256,8 @@ def make_conv_desc(n, h_in, w_in, cin0, cout, kh, kw, stride=1, pad=0, dil=1, ci
         w_out = (w_in + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     return ConvDesc(n=n, h_in=h_in, w_in=w_in, h_out=h_out, w_out=w_out, cin0=cin0, cin1=cin1, cout=cout,
                     kh=kh, kw=kw, stride=stride, pad=pad, dil=dil, transposed=1 if transposed else 0,
-                    split=1 if split else 0, rowk=1 if rowk else 0, row_pitch=row_pitch, n_tile=n_tile)
+                    split=1 if split else 0, rowk=1 if rowk else 0, row_pitch=row_pitch, n_tile=n_tile,
+                    halo=1 if halo else 0)
 
 
 def instance_stats_nhwc(x, stats=None):

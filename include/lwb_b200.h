@@ -40,10 +40,11 @@ int         lwb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * per-face inverse matrices (caller zero-fills, culled faces are left untouched).
  * flip_rows = 0 gives the native kernel's row order (row 0 = bottom, +y up); flip_rows = 1 writes
  * row (H-1-y) instead, i.e. folds the torch.flip of rasterize.py:334-338 into the store.
- * workspace: lwb_raster_workspace_bytes(batch, image_size) bytes of device scratch (z-buffer).
+ * workspace: lwb_raster_workspace_bytes(batch, image_size, num_faces) bytes of device scratch
+ * (64-bit z-buffer + a queue for degenerate faces that need a whole-image scan).
  * face_index_map is bit-exact with the reference kernels compiled by the same nvcc.
  * ------------------------------------------------------------------------------------------ */
-size_t lwb_raster_workspace_bytes(int batch, int image_size);
+size_t lwb_raster_workspace_bytes(int batch, int image_size, int num_faces);
 int lwb_raster_forward_face_index_map(
         const float* faces /* [B,F,3,3] */, int batch, int num_faces, int image_size,
         float near, float far,
@@ -124,6 +125,8 @@ typedef struct lwb_conv_desc {
     int rowk;                 /* 1 = 7x7-stem row-K mode: input is a padded NHWC8 buffer (see conv_tc.cu) */
     int row_pitch;            /* rowk: pixels per padded row (>= w_in + 8) */
     int n_tile;               /* 0 = auto; else force the N tile (16/64/128/256, must divide cout) */
+    int halo;                 /* 1 = halo variant (stride-1 'same' k x k convs and the row-K stem): the activation
+                                 tile + halo is staged once per 64-channel chunk and every tap reads a shifted window */
 } lwb_conv_desc;
 
 /* A plan owns the TMA descriptors of one conv layer bound to fixed device buffers; creating it

@@ -27,7 +27,7 @@ def report(name, got, ref):
     return d.max().item() / scale
 
 
-def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x1=None, n_tile=0, stats=True):
+def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x1=None, n_tile=0, stats=True, halo=False):
     """x [n,c,h,w] fp32 CPU, w OIHW (or IOHW when transposed) -> NCHW fp32 CPU result, stats."""
     n, c0, h, wd = x.shape
     xs = K.nchw_to_nhwc_split(x.to(cuda), split=split)
@@ -36,7 +36,8 @@ def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x
     cout = w.shape[1] if transposed else w.shape[0]
     kh, kw = w.shape[2:]
     d = K.make_conv_desc(n, h, wd, c0, cout, kh, kw, stride=stride, pad=pad, dil=dil,
-                         cin1=0 if x1 is None else x1.shape[1], transposed=transposed, split=split, n_tile=n_tile)
+                         cin1=0 if x1 is None else x1.shape[1], transposed=transposed, split=split, n_tile=n_tile,
+                         halo=halo)
     out = torch.full((n, d.h_out, d.w_out, cout), float("nan"), dtype=torch.float32, device=cuda)
     st = torch.zeros((n, cout, 2), dtype=torch.float64, device=cuda) if stats else None
     plan = K.ConvPlan(d, xs, x1s, ws, out, st)
@@ -83,6 +84,37 @@ def test_conv2d(cuda, case, split):
         check_stats(st, ref)
 
 
+HALO_CASES = [c for c in CASES if c[7] == 1 and c[6] in (3, 7) and c[8] == c[6] // 2] + [
+    ("7x7_64_16_heads", 2, 64, 16, 48, 40, 7, 1, 3, 16),
+    ("5x5_64_64", 1, 64, 64, 32, 32, 5, 1, 2, 0),
+    ("3x3_128_64_64x64", 2, 128, 64, 64, 64, 3, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])
+def test_conv2d_halo(cuda, case, split):
+    """Halo variant: one activation tile (+halo) per chunk, every tap a shifted UMMA descriptor window."""
+    name, n, cin, cout, h, w, k, stride, pad, n_tile = case
+    x = rnd(n, cin, h, w, seed=31)
+    wt = rnd(cout, cin, k, k, seed=32, scale=0.05)
+    ref = F.conv2d(x, wt, stride=1, padding=pad)
+    got, st = run_conv(cuda, x, wt, stride=1, pad=pad, split=split, n_tile=n_tile, halo=True)
+    rel = report(name + "/halo" + ("/split" if split else "/fast"), got, ref)
+    assert rel < (2e-4 if split else 2e-2)
+    if split:
+        check_stats(st, ref)
+
+
+@pytest.mark.parametrize("split", [True, False])
+def test_conv_concat_inputs_halo(cuda, split):
+    a, b = rnd(2, 64, 32, 32, seed=5), rnd(2, 128, 32, 32, seed=6)
+    wt = rnd(64, 192, 3, 3, seed=7, scale=0.05)
+    ref = F.conv2d(torch.cat([a, b], dim=1), wt, padding=1)
+    got, _ = run_conv(cuda, a, wt, split=split, x1=b, halo=True)
+    assert report("concat/halo", got, ref) < (2e-4 if split else 2e-2)
+
+
 @pytest.mark.parametrize("split", [True, False])
 def test_conv_transpose(cuda, split):
     for cin, cout, h in ((128, 64, 32), (512, 256, 32)):
@@ -106,9 +138,10 @@ def test_conv_concat_inputs(cuda, split):
     assert report("concat", got, ref) < (2e-4 if split else 2e-2)
 
 
+@pytest.mark.parametrize("halo", [False, True])
 @pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("size", [32, 256])
-def test_stem_7x7_rowk(cuda, split, size):
+def test_stem_7x7_rowk(cuda, split, size, halo):
     """7x7 stem (6 -> 64 channels) through the row-K layout (networks/generator.py:80-84)."""
     n = 2
     x = rnd(n, 6, size, size, seed=8)
@@ -117,7 +150,7 @@ def test_stem_7x7_rowk(cuda, split, size):
     pitch = size + 8
     xs = K.nchw_to_nhwc_split(x.to(cuda), c_pad=8, pad_hw=(3, 3, 3, 5), split=split)
     ws = K.pack_conv_weight_rowk(wt.to(cuda), split=split)
-    d = K.make_conv_desc(n, size, size, 8, 64, 7, 7, stride=1, pad=3, split=split, rowk=True, row_pitch=pitch)
+    d = K.make_conv_desc(n, size, size, 8, 64, 7, 7, stride=1, pad=3, split=split, rowk=True, row_pitch=pitch, halo=halo)
     out = torch.full((n, size, size, 64), float("nan"), dtype=torch.float32, device=cuda)
     st = torch.zeros((n, 64, 2), dtype=torch.float64, device=cuda)
     K.ConvPlan(d, xs, None, ws, out, st).run()
