@@ -30,6 +30,8 @@
 // per column per tile).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -371,6 +373,7 @@ struct HaloParams {
     int a_plane_bytes;                // a_rows * pitch_bytes (one of hi / lo)
     int a_stage_bytes;                // a_plane_bytes * (SPLIT ? 2 : 1)
     int nb_stages;
+    int bo_mode;                      // descriptor base_offset for a kx-shifted window: 0 none, 1 +kx, 2 -kx (diagnostic)
     float* out; int out_h, out_w, cout;
     int oy_mul, oy_add, ox_mul, ox_add;
     double* stats;
@@ -484,16 +487,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
                         tc_fence_after();
                         const int ky = tap / P.kw, kx = tap - ky * P.kw;
                         const uint32_t a_off = (uint32_t)(ky * P.pitch_bytes + kx * 128);
+                        const uint32_t bo = P.bo_mode == 1 ? (uint32_t)kx : (P.bo_mode == 2 ? (uint32_t)((8 - kx) & 7) : 0u);
                         const uint32_t b_hi = b_ring_u + sb * B_STAGE;
                         const uint32_t b_lo = b_hi + B_BYTES;
 #pragma unroll
                         for (int k = 0; k < KCHUNK / 16; k++) {
-                            const uint64_t da = make_desc_ex(a_hi + a_off + k * 32, (uint32_t)P.pitch_bytes, (uint32_t)kx);
+                            const uint64_t da = make_desc_ex(a_hi + a_off + k * 32, (uint32_t)P.pitch_bytes, bo);
                             const uint64_t db = make_desc(b_hi + k * 32);
                             umma_f16(d_tmem, da, db, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
                             if (SPLIT) {
                                 umma_f16(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
-                                umma_f16(d_tmem, make_desc_ex(a_lo + a_off + k * 32, (uint32_t)P.pitch_bytes, (uint32_t)kx), db, idesc, 1u);
+                                umma_f16(d_tmem, make_desc_ex(a_lo + a_off + k * 32, (uint32_t)P.pitch_bytes, bo), db, idesc, 1u);
                             }
                         }
                         umma_commit(bar_bempty + sb);
@@ -710,10 +714,10 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
             if (split && (rc = encode_map(&h.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
             h.chunks0 = 1; h.chunks1 = 0;
         } else {
-            LWB_CHECK_ARG(d->kw <= 9 && d->kh == d->kw && d->pad == d->kh / 2, "halo mode needs an odd square kernel <= 9 with 'same' padding");
+            LWB_CHECK_ARG(d->kw <= 9 && (d->kw & 1) && (d->kh & 1), "halo mode needs an odd kernel, kw <= 9, with 'same' padding (kh/2, kw/2)");
             LWB_CHECK_ARG(d->cin0 % KCHUNK == 0 && d->cin1 % KCHUNK == 0 && d->cin0 > 0, "input channels must be multiples of 64");
             LWB_CHECK_ARG(d->cin1 == 0 || (x1_hi && (!split || x1_lo)), "second input missing");
-            h.kh = d->kh; h.kw = d->kw; h.x_off = -d->pad; h.y_off = -d->pad;
+            h.kh = d->kh; h.kw = d->kw; h.x_off = -(d->kw / 2); h.y_off = -(d->kh / 2);
             h.a_rows = TILE_H + d->kh - 1; h.pitch_bytes = 16 * 128;
             auto amap = [&](CUtensorMap* m, const uint16_t* base, int c) {
                 const uint64_t dims[4] = {(uint64_t)c, (uint64_t)d->w_in, (uint64_t)d->h_in, (uint64_t)d->n};
@@ -735,6 +739,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
             if (split && (rc = encode_map(&h.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
             h.chunks0 = d->cin0 / KCHUNK; h.chunks1 = d->cin1 / KCHUNK;
         }
+        { const char* e = getenv("LWB_HALO_BO"); h.bo_mode = e ? atoi(e) : 1; }
         h.a_plane_bytes = h.a_rows * h.pitch_bytes;
         h.a_stage_bytes = h.a_plane_bytes * (split ? 2 : 1);
         const int fixed = 1024 + HALO_NA * h.a_stage_bytes + 256 + 4 * n_tile * 8;
