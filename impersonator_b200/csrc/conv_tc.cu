@@ -351,9 +351,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
 // Halo variant (stride-1 k x k convs, and the row-K stem): the activation tile is fetched ONCE per
 // 64-channel chunk together with its halo -- (16 + kh - 1) rows of 16 pixels (8 + kw - 1 <= 16) -- and
 // every filter tap reads a shifted window of that one shared-memory tile through the UMMA descriptor:
-//   start address = tile + ky * pitch + kx * 128 B,  8-row-group stride (SBO) = pitch = 16 px * 128 B,
-//   descriptor base_offset = kx  (the 128B-swizzle phase of the first row, since the window no longer
-//   starts on a 1024 B boundary: phase = (address >> 7) & 7).
+//   start address = tile + ky * pitch + kx * 128 B,  8-row-group stride (SBO) = pitch = 16 px * 128 B.
+//   The window then no longer starts on a 1024 B swizzle-atom boundary; measured on B200
+//   (tools/halo_diag.py): the tensor core derives the 128B-swizzle phase from the ADDRESS bits
+//   [7:9] of every row it fetches -- exactly what TMA used when it wrote the tile -- so the
+//   descriptor's base_offset field must stay 0 (setting it to kx or -kx gives garbage).
 // Activation traffic L2->SMEM drops from taps x 16 KB to (16+kh-1) x 2 KB per chunk (3x3: 4x less,
 // 7x7: 17x less); weights stream per (chunk, tap) through their own ring.  This is what makes the
 // narrow layers (Cout = 64 at 256^2, the 7x7 heads) tensor-bound instead of L2-bound.
@@ -373,7 +375,7 @@ struct HaloParams {
     int a_plane_bytes;                // a_rows * pitch_bytes (one of hi / lo)
     int a_stage_bytes;                // a_plane_bytes * (SPLIT ? 2 : 1)
     int nb_stages;
-    int bo_mode;                      // descriptor base_offset for a kx-shifted window: 0 none, 1 +kx, 2 -kx (diagnostic)
+    int bo_mode;                      // descriptor base_offset for a kx-shifted window: 0 (correct), 1 +kx, 2 -kx (LWB_HALO_BO, diagnostic only)
     float* out; int out_h, out_w, cout;
     int oy_mul, oy_add, ox_mul, ox_add;
     double* stats;
@@ -739,7 +741,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
             if (split && (rc = encode_map(&h.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
             h.chunks0 = d->cin0 / KCHUNK; h.chunks1 = d->cin1 / KCHUNK;
         }
-        { const char* e = getenv("LWB_HALO_BO"); h.bo_mode = e ? atoi(e) : 1; }
+        { const char* e = getenv("LWB_HALO_BO"); h.bo_mode = e ? atoi(e) : 0; }
         h.a_plane_bytes = h.a_rows * h.pitch_bytes;
         h.a_stage_bytes = h.a_plane_bytes * (split ? 2 : 1);
         const int fixed = 1024 + HALO_NA * h.a_stage_bytes + 256 + 4 * n_tile * 8;
