@@ -438,32 +438,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
 
     if (warp == 0) {
         // ================================ TMA producer =================================
+        // Work items = (tile, chunk) in execution order.  The activation halo of item i+1 is requested
+        // BEFORE the weight taps of item i are streamed, so the big A transfer has a whole chunk of MMA
+        // time to land (the weight ring alone would only let it start 2-4 taps before it is needed).
         if (lane == 0) {
             int sa = 0; uint32_t pa = 0;
             int sb = 0; uint32_t pb = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_idx = tile / m_tiles, m_idx = tile % m_tiles;
+            const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int items = my_tiles * nchunks;
+            auto issue_a = [&](int item) {
+                const int tile = (int)blockIdx.x + (item / nchunks) * (int)gridDim.x;
+                const int chunk = item % nchunks;
+                const int m_idx = tile % m_tiles;
                 const int img = m_idx / (P.tiles_y * P.tiles_x);
                 const int rem = m_idx % (P.tiles_y * P.tiles_x);
                 const int y0 = (rem / P.tiles_x) * TILE_H + P.y_off, x0 = (rem % P.tiles_x) * TILE_W + P.x_off;
-                for (int chunk = 0; chunk < nchunks; chunk++) {
-                    const bool second = chunk >= P.chunks0;
-                    const int mi = second ? 1 : 0;
-                    const int c0 = (second ? chunk - P.chunks0 : chunk) * KCHUNK;
-                    mbar_wait(bar_aempty + sa, pa ^ 1);
-                    uint8_t* sta = a_ring + sa * P.a_stage_bytes;
-                    mbar_expect_tx(bar_afull + sa, (uint32_t)P.a_stage_bytes);
-                    tma_load_4d(&P.a_hi[mi], sta, bar_afull + sa, c0, x0, y0, img);
-                    if (SPLIT) tma_load_4d(&P.a_lo[mi], sta + P.a_plane_bytes, bar_afull + sa, c0, x0, y0, img);
-                    if (++sa == HALO_NA) { sa = 0; pa ^= 1; }
-                    for (int tap = 0; tap < ntaps; tap++) {
-                        mbar_wait(bar_bempty + sb, pb ^ 1);
-                        uint8_t* stb = b_ring + sb * B_STAGE;
-                        mbar_expect_tx(bar_bfull + sb, (uint32_t)B_STAGE);
-                        tma_load_3d(&P.w_hi, stb, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
-                        if (SPLIT) tma_load_3d(&P.w_lo, stb + B_BYTES, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
-                        if (++sb == nb) { sb = 0; pb ^= 1; }
-                    }
+                const bool second = chunk >= P.chunks0;
+                const int mi = second ? 1 : 0;
+                const int c0 = (second ? chunk - P.chunks0 : chunk) * KCHUNK;
+                mbar_wait(bar_aempty + sa, pa ^ 1);
+                uint8_t* sta = a_ring + sa * P.a_stage_bytes;
+                mbar_expect_tx(bar_afull + sa, (uint32_t)P.a_stage_bytes);
+                tma_load_4d(&P.a_hi[mi], sta, bar_afull + sa, c0, x0, y0, img);
+                if (SPLIT) tma_load_4d(&P.a_lo[mi], sta + P.a_plane_bytes, bar_afull + sa, c0, x0, y0, img);
+                if (++sa == HALO_NA) { sa = 0; pa ^= 1; }
+            };
+            if (items > 0) issue_a(0);
+            for (int item = 0; item < items; item++) {
+                if (item + 1 < items) issue_a(item + 1);
+                const int tile = (int)blockIdx.x + (item / nchunks) * (int)gridDim.x;
+                const int chunk = item % nchunks;
+                const int n_idx = tile / m_tiles;
+                for (int tap = 0; tap < ntaps; tap++) {
+                    mbar_wait(bar_bempty + sb, pb ^ 1);
+                    uint8_t* stb = b_ring + sb * B_STAGE;
+                    mbar_expect_tx(bar_bfull + sb, (uint32_t)B_STAGE);
+                    tma_load_3d(&P.w_hi, stb, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
+                    if (SPLIT) tma_load_3d(&P.w_lo, stb + B_BYTES, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
+                    if (++sb == nb) { sb = 0; pb ^= 1; }
                 }
             }
         }
@@ -626,7 +638,7 @@ int launch(const Launch& L, cudaStream_t st)
 int pick_n_tile(int cout, bool split, int forced)
 {
     if (forced > 0) return forced;
-    if (cout % 256 == 0 && !split) return 256;
+    if (cout % 256 == 0) return 256;      // measured on B200: split N=256 (2 stages) 473 TF/s vs N=128 (3 stages) 420
     if (cout % 128 == 0) return 128;
     if (cout % 64 == 0) return 64;
     if (cout % 16 == 0) return 16;
