@@ -132,6 +132,35 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// cluster variants: one CTA's TMA load lands in every CTA of the cluster (same smem offset) and completes
+// tx bytes on each destination CTA's own mbarrier; one commit arrives on every CTA's mbarrier.
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+
+// Persistent tile schedule shared by the three warp roles.  A cluster of CL CTAs takes CL consecutive
+// M tiles of ONE N tile per step ("super tile"), so that the weight tile is common to the cluster.
+struct Sched {
+    int first, step, total, msup, cl, rank;
+    __device__ __forceinline__ void decode(int sup, int& n_idx, int& m_idx) const { n_idx = sup / msup; m_idx = (sup % msup) * cl + rank; }
+};
+__device__ __forceinline__ Sched make_sched(int m_tiles, int n_tiles_n, int cl) {
+    Sched s;
+    s.cl = cl; s.rank = cl > 1 ? (int)cluster_ctarank() : 0;
+    s.msup = m_tiles / cl; s.total = s.msup * n_tiles_n;
+    s.first = (int)blockIdx.x / cl; s.step = (int)gridDim.x / cl;
+    return s;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -175,7 +204,7 @@ __device__ __forceinline__ float warp_col_sums(float* v, unsigned lane) {
 
 // Epilogue warps (4): TMEM accumulator -> fp32 NHWC global + InstanceNorm partial statistics.
 template <int N_TILE, class PT>
-__device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned lane, int total_tiles, int m_tiles,
+__device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned lane, const Sched& sch,
                                               uint32_t tmem_base, uint64_t* bar_tfull, uint64_t* bar_tempty, float2* s_stats)
 {
     const int q = warp & 3;                                     // TMEM lane quarter this warp may access
@@ -183,8 +212,9 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
     const int ty = row >> 3, tx = row & 7;
     const int et = threadIdx.x - 64;                            // 0..127
     int abuf = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_idx = tile / m_tiles, m_idx = tile % m_tiles;
+    for (int sup = sch.first; sup < sch.total; sup += sch.step) {
+        int n_idx, m_idx;
+        sch.decode(sup, n_idx, m_idx);
         const int img = m_idx / (P.tiles_y * P.tiles_x);
         const int rem = m_idx % (P.tiles_y * P.tiles_x);
         const int y = (rem / P.tiles_x) * TILE_H + ty, x = (rem % P.tiles_x) * TILE_W + tx;
@@ -235,7 +265,7 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
 }
 
 // ----------------------------------------------------------------------------------- kernel
-template <int N_TILE, bool SPLIT>
+template <int N_TILE, bool SPLIT, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvParams P)
 {
     using C = Cfg<N_TILE, SPLIT>;
@@ -253,7 +283,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
 
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < C::STAGES; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+            // empty[s] collects one commit from EVERY CTA of the cluster: a stage may be refilled (by
+            // any CTA's multicast) only when all of them have finished reading it.
+            for (int s = 0; s < C::STAGES; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CL); }
             for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + b, 1); mbar_init(bar_tempty + b, 4); }
             fence_barrier_init();
             fence_proxy_async();
@@ -265,20 +297,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();              // peers' barriers are initialised before any multicast can land
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int nchunks = P.chunks0 + P.chunks1;
     const int ksteps = P.ntaps * nchunks;
     const int m_tiles = P.n_img * P.tiles_y * P.tiles_x;
-    const int total_tiles = m_tiles * P.n_tiles_n;
+    const Sched sch = make_sched(m_tiles, P.n_tiles_n, CL);
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    constexpr int B_SLICE = N_TILE / CL;         // weight rows this CTA fetches (and multicasts) per stage
 
     if (warp == 0) {
         // ================================ TMA producer =================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_idx = tile / m_tiles, m_idx = tile % m_tiles;
+            for (int sup = sch.first; sup < sch.total; sup += sch.step) {
+                int n_idx, m_idx;
+                sch.decode(sup, n_idx, m_idx);
                 const int img = m_idx / (P.tiles_y * P.tiles_x);
                 const int rem = m_idx % (P.tiles_y * P.tiles_x);
                 const int y0 = (rem / P.tiles_x) * TILE_H, x0 = (rem % P.tiles_x) * TILE_W;
@@ -294,8 +330,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                     tma_load_4d(&P.a_hi[mi], st, bar_full + stage, c0, xx, yy, img);
                     if (SPLIT) tma_load_4d(&P.a_lo[mi], st + A_BYTES, bar_full + stage, c0, xx, yy, img);
                     uint8_t* sb = st + A_BYTES * (SPLIT ? 2 : 1);
-                    tma_load_3d(&P.w_hi, sb, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE, P.wtap[tap]);
-                    if (SPLIT) tma_load_3d(&P.w_lo, sb + C::B_BYTES, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE, P.wtap[tap]);
+                    if (CL == 1) {
+                        tma_load_3d(&P.w_hi, sb, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE, P.wtap[tap]);
+                        if (SPLIT) tma_load_3d(&P.w_lo, sb + C::B_BYTES, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE, P.wtap[tap]);
+                    } else {
+                        const int r0 = sch.rank * B_SLICE;
+                        tma_load_3d_mc(&P.w_hi, sb + r0 * 128, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE + r0, P.wtap[tap], kMask);
+                        if (SPLIT) tma_load_3d_mc(&P.w_lo, sb + C::B_BYTES + r0 * 128, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE + r0, P.wtap[tap], kMask);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -307,7 +349,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int abuf = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int sup = sch.first; sup < sch.total; sup += sch.step) {
                 mbar_wait(bar_tempty + abuf, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * N_TILE);
@@ -327,7 +369,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                             umma_f16(d_tmem, make_desc(a_lo + k * 32), db, idesc, 1u);
                         }
                     }
-                    umma_commit(bar_empty + stage);                 // smem slot free once these MMAs retire
+                    // smem slot free (in every CTA of the cluster) once these MMAs retire
+                    if (CL == 1) umma_commit(bar_empty + stage); else umma_commit_mc(bar_empty + stage, kMask);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(bar_tfull + abuf);                      // accumulator complete -> epilogue
@@ -336,13 +379,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
         }
     } else {
         // ================================ epilogue (4 warps) ===========================
-        epilogue_loop<N_TILE>(P, warp, lane, total_tiles, m_tiles, tmem_base, bar_tfull, bar_tempty, s_stats);
+        epilogue_loop<N_TILE>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();              // nobody exits while a peer may still multicast into it
     tc_fence_after();
     if (warp == 1) {
+        __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
     }
 }
@@ -525,7 +570,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
             }
         }
     } else {
-        epilogue_loop<N_TILE>(P, warp, lane, total_tiles, m_tiles, tmem_base, bar_tfull, bar_tempty, s_stats);
+        const Sched sch = make_sched(m_tiles, P.n_tiles_n, 1);
+        epilogue_loop<N_TILE>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
     }
 
     tc_fence_before();
@@ -583,6 +629,7 @@ struct Launch {
     int halo_smem;
     int n_tile;
     bool split;
+    int cl;
     int grid;
 };
 
@@ -599,18 +646,36 @@ int launch_halo_one(const Launch& L, cudaStream_t st)
     return LWB_OK;
 }
 
-template <int N_TILE, bool SPLIT>
-int launch_one(const Launch& L, cudaStream_t st)
+template <int N_TILE, bool SPLIT, int CL>
+int launch_cl(const Launch& L, cudaStream_t st)
 {
     using C = Cfg<N_TILE, SPLIT>;
     static bool attr_set = false;
     if (!attr_set) {
-        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<N_TILE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<N_TILE, SPLIT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    k_conv_tc<N_TILE, SPLIT><<<L.grid, NUM_THREADS, C::SMEM_BYTES, st>>>(L.p);
+    if (CL == 1) {
+        k_conv_tc<N_TILE, SPLIT, CL><<<L.grid, NUM_THREADS, C::SMEM_BYTES, st>>>(L.p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        LWB_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tc<N_TILE, SPLIT, CL>, L.p));
+    }
     LWB_LAUNCH_OK();
     return LWB_OK;
+}
+
+template <int N_TILE, bool SPLIT>
+int launch_one(const Launch& L, cudaStream_t st)
+{
+    if (L.cl == 2) return launch_cl<N_TILE, SPLIT, 2>(L, st);
+    if (L.cl == 4 && N_TILE >= 32) return launch_cl<N_TILE, SPLIT, (N_TILE >= 32 ? 4 : 1)>(L, st);
+    return launch_cl<N_TILE, SPLIT, 1>(L, st);
 }
 
 int launch(const Launch& L, cudaStream_t st)
@@ -683,6 +748,16 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     const int n_tile = pick_n_tile(d->cout, split, d->n_tile);
     LWB_CHECK_ARG(n_tile > 0 && d->cout % n_tile == 0, "no N tile divides cout");
 
+    // Cluster size for weight-tile multicast (LWB_CLUSTER = 1 | 2 | 4, default 2): the CTAs of a cluster work on
+    // consecutive M tiles of the same N tile, each fetches 1/CL of the weight tile and multicasts it.
+    const int dom_h0 = d->transposed ? d->h_in : d->h_out, dom_w0 = d->transposed ? d->w_in : d->w_out;
+    const long m_tiles0 = (long)d->n * lwb::ceil_div(dom_h0, TILE_H) * lwb::ceil_div(dom_w0, TILE_W);
+    int cl = 2;
+    { const char* e = getenv("LWB_CLUSTER"); if (e) cl = atoi(e); }
+    if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+    while (cl > 1 && (m_tiles0 % cl != 0 || (n_tile / cl) % 8 != 0 || n_tile / cl < 8)) cl >>= 1;
+    if (d->halo) cl = 1;
+
     lwb_conv_plan* plan = new (std::nothrow) lwb_conv_plan();
     LWB_CHECK_ARG(plan, "out of host memory");
     plan->num = 0;
@@ -698,9 +773,10 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.n_tiles_n = d->cout / n_tile;
         p.out = out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
-        L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0;
-        const long total = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
-        L.grid = (int)(total < sms ? total : sms);
+        L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl;
+        const long total_super = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n / cl;
+        const long max_clusters = sms / cl;
+        L.grid = (int)((total_super < max_clusters ? total_super : max_clusters) * cl);
     };
 
     if (d->halo) {
@@ -768,7 +844,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         h.out = out_raw; h.out_h = d->h_out; h.out_w = d->w_out; h.cout = d->cout;
         h.oy_mul = 1; h.ox_mul = 1; h.oy_add = 0; h.ox_add = 0;
         h.stats = stats;
-        L.n_tile = n_tile; L.split = split;
+        L.n_tile = n_tile; L.split = split; L.cl = 1;
         const long total = (long)h.n_img * h.tiles_y * h.tiles_x * h.n_tiles_n;
         L.grid = (int)(total < sms ? total : sms);
         *plan_out = plan;
@@ -791,7 +867,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         if (split && (rc = encode_map(&L.p.a_lo[0], x0_lo, 4, dims, str, box)) != LWB_OK) return fail(rc);
         const uint64_t wd[3] = {64, (uint64_t)d->cout, (uint64_t)d->kh};
         const uint64_t ws[2] = {128, (uint64_t)d->cout * 128};
-        const uint32_t wb[3] = {KCHUNK, (uint32_t)n_tile, 1};
+        const uint32_t wb[3] = {KCHUNK, (uint32_t)(n_tile / cl), 1};
         if ((rc = encode_map(&L.p.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
         if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
         L.p.ntaps = d->kh; L.p.chunks0 = 1; L.p.chunks1 = 0;
@@ -809,7 +885,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     LWB_CHECK_ARG(ntaps_w <= MAX_TAPS, "too many filter taps");
     const uint64_t wd[3] = {(uint64_t)cin_total, (uint64_t)d->cout, (uint64_t)ntaps_w};
     const uint64_t ws[2] = {(uint64_t)cin_total * 2, (uint64_t)d->cout * cin_total * 2};
-    const uint32_t wb[3] = {KCHUNK, (uint32_t)n_tile, 1};
+    const uint32_t wb[3] = {KCHUNK, (uint32_t)(n_tile / cl), 1};
 
     if (d->transposed) {
         // ConvTranspose2d(k=3, s=2, p=1, output_padding=1): out[2i+a, 2j+b] gathers, per axis,

@@ -35,8 +35,8 @@ def bench(name, n, cin, cout, h, k, stats=True, halo=False, n_tile=0, split=True
     print("%-44s stats=%d halo=%d ntile=%3d : %7.3f ms  %7.1f TF/s algorithmic" % (name, stats, halo, n_tile or -1, ms, plan.flops / ms / 1e9))
 
 
-for stats in (True, False):
-    for halo in (False, True):
+for stats in (True,):
+    for halo in (False,):
         bench("stem rowk 8->64 @256 B16", 16, 8, 64, 256, 7, stats=stats, halo=halo, rowk=True)
         bench("skipper 64+64->64 @256 B16", 16, 64, 64, 256, 3, stats=stats, halo=halo, cin1=64)
         bench("skipper 128+128->128 @128 B16", 16, 128, 128, 128, 3, stats=stats, halo=halo, cin1=128)
