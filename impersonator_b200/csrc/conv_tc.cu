@@ -57,6 +57,7 @@ struct ConvParams {
     float* out; int out_h, out_w, cout;
     int oy_mul, oy_add, ox_mul, ox_add;
     double* stats;
+    int stages;                       // pipeline depth actually used (<= Cfg::STAGES; LWB_STAGES, diagnostic)
 };
 
 template <int N_TILE, bool SPLIT>
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
 
     const int nchunks = P.chunks0 + P.chunks1;
     const int ksteps = P.ntaps * nchunks;
+    const int nstages = P.stages;
     const int m_tiles = P.n_img * P.tiles_y * P.tiles_x;
     const Sched sch = make_sched(m_tiles, P.n_tiles_n, CL);
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
@@ -311,6 +313,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     if (warp == 0) {
         // ================================ TMA producer =================================
         if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&P.a_hi[0]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" :: "l"(&P.w_hi) : "memory");
+            if (SPLIT) {
+                asm volatile("prefetch.tensormap [%0];" :: "l"(&P.a_lo[0]) : "memory");
+                asm volatile("prefetch.tensormap [%0];" :: "l"(&P.w_lo) : "memory");
+            }
             int stage = 0; uint32_t phase = 0;
             for (int sup = sch.first; sup < sch.total; sup += sch.step) {
                 int n_idx, m_idx;
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                         tma_load_3d_mc(&P.w_hi, sb + r0 * 128, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE + r0, P.wtap[tap], kMask);
                         if (SPLIT) tma_load_3d_mc(&P.w_lo, sb + C::B_BYTES + r0 * 128, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE + r0, P.wtap[tap], kMask);
                     }
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                     }
                     // smem slot free (in every CTA of the cluster) once these MMAs retire
                     if (CL == 1) umma_commit(bar_empty + stage); else umma_commit_mc(bar_empty + stage, kMask);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(bar_tfull + abuf);                      // accumulator complete -> epilogue
                 if (++abuf == 2) { abuf = 0; aphase ^= 1; }
@@ -655,6 +663,9 @@ int launch_cl(const Launch& L, cudaStream_t st)
         LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<N_TILE, SPLIT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
+    ConvParams& pp = const_cast<ConvParams&>(L.p);
+    { static int forced = -1; if (forced < 0) { const char* e = getenv("LWB_STAGES"); forced = e ? atoi(e) : 0; }
+      pp.stages = (forced >= 2 && forced < C::STAGES) ? forced : C::STAGES; }
     if (CL == 1) {
         k_conv_tc<N_TILE, SPLIT, CL><<<L.grid, NUM_THREADS, C::SMEM_BYTES, st>>>(L.p);
     } else {
@@ -748,11 +759,13 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     const int n_tile = pick_n_tile(d->cout, split, d->n_tile);
     LWB_CHECK_ARG(n_tile > 0 && d->cout % n_tile == 0, "no N tile divides cout");
 
-    // Cluster size for weight-tile multicast (LWB_CLUSTER = 1 | 2 | 4, default 2): the CTAs of a cluster work on
+    // Cluster size for weight-tile multicast (LWB_CLUSTER = 1 | 2 | 4, default 1): the CTAs of a cluster work on
     // consecutive M tiles of the same N tile, each fetches 1/CL of the weight tile and multicasts it.
+    // Measured on B200 (tools/conv_microbench.py): CL=2 is within 2% of CL=1 on every layer, CL=4 is slower --
+    // weight-tile L2 traffic is not what bounds this kernel -- so the plain launch stays the default.
     const int dom_h0 = d->transposed ? d->h_in : d->h_out, dom_w0 = d->transposed ? d->w_in : d->w_out;
     const long m_tiles0 = (long)d->n * lwb::ceil_div(dom_h0, TILE_H) * lwb::ceil_div(dom_w0, TILE_W);
-    int cl = 2;
+    int cl = 1;
     { const char* e = getenv("LWB_CLUSTER"); if (e) cl = atoi(e); }
     if (cl != 1 && cl != 2 && cl != 4) cl = 1;
     while (cl > 1 && (m_tiles0 % cl != 0 || (n_tile / cl) % 8 != 0 || n_tile / cl < 8)) cl >>= 1;
@@ -774,6 +787,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.out = out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
         L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl;
+        p.stages = 64;      // clamped to Cfg::STAGES at launch
         const long total_super = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n / cl;
         const long max_clusters = sms / cl;
         L.grid = (int)((total_super < max_clusters ? total_super : max_clusters) * cl);

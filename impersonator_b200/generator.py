@@ -44,10 +44,11 @@ def _align_corners():
 
 
 def _halo_mode():
-    """LWB_HALO: 'auto' (default) = halo variant of the conv kernel where it pays (row-K stem, the
-    skippers, the 7x7 heads on tensor cores); '0' = never (per-tap TMA loads, CUDA-core heads);
-    'all' = also the 512-channel residual blocks."""
-    return os.environ.get("LWB_HALO", "auto")
+    """LWB_HALO: '0' (default) = per-tap TMA loads + CUDA-core 7x7 heads; 'auto' = halo variant of the conv
+    kernel for the row-K stem and the skippers + 7x7 heads on tensor cores; 'all' = also the residual blocks.
+    The halo variant is correct (tests/test_conv_gpu.py) but measured 10-30% SLOWER than per-tap loads on B200
+    and the N=16 tensor-core heads 3x slower than the CUDA-core kernel, hence the default."""
+    return os.environ.get("LWB_HALO", "0")
 
 
 class NetworkBase(nn.Module):
