@@ -60,10 +60,12 @@ struct ConvParams {
     int stages;                       // pipeline depth actually used (<= Cfg::STAGES; LWB_STAGES, diagnostic)
 };
 
-template <int N_TILE, bool SPLIT>
+template <int N_TILE, bool SPLIT, int KC = KCHUNK>
 struct Cfg {
-    static constexpr int B_BYTES = N_TILE * 128;
-    static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+    static constexpr int ROW_BYTES = KC * 2;                 // one operand row of a stage (128 B or 64 B)
+    static constexpr int A_TILE = 128 * ROW_BYTES;
+    static constexpr int B_BYTES = N_TILE * ROW_BYTES;
+    static constexpr int STAGE_BYTES = (A_TILE + B_BYTES) * (SPLIT ? 2 : 1);
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128
@@ -124,6 +126,13 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* dst, u
 // SBO(=1024B>>4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Same for a K stage of KC fp16: KC = 64 -> 128 B rows, SWIZZLE_128B (2), 8-row group = 1024 B;
+//                               KC = 32 ->  64 B rows, SWIZZLE_64B  (4), 8-row group =  512 B.
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)((8 * KC * 2) >> 4) << 32) | (1ull << 46)
+         | ((KC == 64 ? 2ull : 4ull) << 61);
 }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -266,10 +275,10 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
 }
 
 // ----------------------------------------------------------------------------------- kernel
-template <int N_TILE, bool SPLIT, int CL>
+template <int N_TILE, bool SPLIT, int CL, int KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvParams P)
 {
-    using C = Cfg<N_TILE, SPLIT>;
+    using C = Cfg<N_TILE, SPLIT, KC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -333,18 +342,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                     const int tap = s / nchunks, chunk = s % nchunks;
                     const bool second = chunk >= P.chunks0;
                     const int mi = second ? 1 : P.tmap[tap];
-                    const int c0 = (second ? chunk - P.chunks0 : chunk) * KCHUNK;
+                    const int c0 = (second ? chunk - P.chunks0 : chunk) * KC;
                     const int xx = x0 + P.dx[tap], yy = y0 + P.dy[tap];
                     tma_load_4d(&P.a_hi[mi], st, bar_full + stage, c0, xx, yy, img);
-                    if (SPLIT) tma_load_4d(&P.a_lo[mi], st + A_BYTES, bar_full + stage, c0, xx, yy, img);
-                    uint8_t* sb = st + A_BYTES * (SPLIT ? 2 : 1);
+                    if (SPLIT) tma_load_4d(&P.a_lo[mi], st + C::A_TILE, bar_full + stage, c0, xx, yy, img);
+                    uint8_t* sb = st + C::A_TILE * (SPLIT ? 2 : 1);
                     if (CL == 1) {
-                        tma_load_3d(&P.w_hi, sb, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE, P.wtap[tap]);
-                        if (SPLIT) tma_load_3d(&P.w_lo, sb + C::B_BYTES, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE, P.wtap[tap]);
+                        tma_load_3d(&P.w_hi, sb, bar_full + stage, chunk * KC, n_idx * N_TILE, P.wtap[tap]);
+                        if (SPLIT) tma_load_3d(&P.w_lo, sb + C::B_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE, P.wtap[tap]);
                     } else {
                         const int r0 = sch.rank * B_SLICE;
-                        tma_load_3d_mc(&P.w_hi, sb + r0 * 128, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE + r0, P.wtap[tap], kMask);
-                        if (SPLIT) tma_load_3d_mc(&P.w_lo, sb + C::B_BYTES + r0 * 128, bar_full + stage, chunk * KCHUNK, n_idx * N_TILE + r0, P.wtap[tap], kMask);
+                        tma_load_3d_mc(&P.w_hi, sb + r0 * C::ROW_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE + r0, P.wtap[tap], kMask);
+                        if (SPLIT) tma_load_3d_mc(&P.w_lo, sb + C::B_BYTES + r0 * C::ROW_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE + r0, P.wtap[tap], kMask);
                     }
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
@@ -365,16 +374,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                     mbar_wait(bar_full + stage, phase);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
-                    const uint32_t a_lo = a_hi + A_BYTES;
-                    const uint32_t b_hi = a_hi + A_BYTES * (SPLIT ? 2 : 1);
+                    const uint32_t a_lo = a_hi + C::A_TILE;
+                    const uint32_t b_hi = a_hi + C::A_TILE * (SPLIT ? 2 : 1);
                     const uint32_t b_lo = b_hi + C::B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < KCHUNK / 16; k++) {
-                        const uint64_t da = make_desc(a_hi + k * 32), db = make_desc(b_hi + k * 32);
+                    for (int k = 0; k < KC / 16; k++) {
+                        const uint64_t da = make_desc_k<KC>(a_hi + k * 32), db = make_desc_k<KC>(b_hi + k * 32);
                         umma_f16(d_tmem, da, db, idesc, (s > 0 || k > 0) ? 1u : 0u);
                         if (SPLIT) {
-                            umma_f16(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
-                            umma_f16(d_tmem, make_desc(a_lo + k * 32), db, idesc, 1u);
+                            umma_f16(d_tmem, da, make_desc_k<KC>(b_lo + k * 32), idesc, 1u);
+                            umma_f16(d_tmem, make_desc_k<KC>(a_lo + k * 32), db, idesc, 1u);
                         }
                     }
                     // smem slot free (in every CTA of the cluster) once these MMAs retire
@@ -617,7 +626,8 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
     for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i < rank - 1; i++) gstr[i] = strides_bytes[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box[0] == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         lwb::set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] strides [%llu,%llu,%llu] box [%u,%u,%u,%u]",
@@ -638,6 +648,7 @@ struct Launch {
     int n_tile;
     bool split;
     int cl;
+    int kc;
     int grid;
 };
 
@@ -654,20 +665,20 @@ int launch_halo_one(const Launch& L, cudaStream_t st)
     return LWB_OK;
 }
 
-template <int N_TILE, bool SPLIT, int CL>
+template <int N_TILE, bool SPLIT, int CL, int KC>
 int launch_cl(const Launch& L, cudaStream_t st)
 {
-    using C = Cfg<N_TILE, SPLIT>;
+    using C = Cfg<N_TILE, SPLIT, KC>;
     static bool attr_set = false;
     if (!attr_set) {
-        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<N_TILE, SPLIT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<N_TILE, SPLIT, CL, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     ConvParams& pp = const_cast<ConvParams&>(L.p);
     { static int forced = -1; if (forced < 0) { const char* e = getenv("LWB_STAGES"); forced = e ? atoi(e) : 0; }
       pp.stages = (forced >= 2 && forced < C::STAGES) ? forced : C::STAGES; }
     if (CL == 1) {
-        k_conv_tc<N_TILE, SPLIT, CL><<<L.grid, NUM_THREADS, C::SMEM_BYTES, st>>>(L.p);
+        k_conv_tc<N_TILE, SPLIT, CL, KC><<<L.grid, NUM_THREADS, C::SMEM_BYTES, st>>>(L.p);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
@@ -675,7 +686,7 @@ int launch_cl(const Launch& L, cudaStream_t st)
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        LWB_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tc<N_TILE, SPLIT, CL>, L.p));
+        LWB_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tc<N_TILE, SPLIT, CL, KC>, L.p));
     }
     LWB_LAUNCH_OK();
     return LWB_OK;
@@ -684,9 +695,10 @@ int launch_cl(const Launch& L, cudaStream_t st)
 template <int N_TILE, bool SPLIT>
 int launch_one(const Launch& L, cudaStream_t st)
 {
-    if (L.cl == 2) return launch_cl<N_TILE, SPLIT, 2>(L, st);
-    if (L.cl == 4 && N_TILE >= 32) return launch_cl<N_TILE, SPLIT, (N_TILE >= 32 ? 4 : 1)>(L, st);
-    return launch_cl<N_TILE, SPLIT, 1>(L, st);
+    if (L.kc == 32) return launch_cl<N_TILE, SPLIT, 1, 32>(L, st);
+    if (L.cl == 2) return launch_cl<N_TILE, SPLIT, 2, 64>(L, st);
+    if (L.cl == 4 && N_TILE >= 32) return launch_cl<N_TILE, SPLIT, (N_TILE >= 32 ? 4 : 1), 64>(L, st);
+    return launch_cl<N_TILE, SPLIT, 1, 64>(L, st);
 }
 
 int launch(const Launch& L, cudaStream_t st)
@@ -729,19 +741,19 @@ struct lwb_conv_plan {
 };
 
 // Plain NHWC activation map: dims [C, W, H, N].
-static int map_nhwc(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c)
+static int map_nhwc(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c, int kc = KCHUNK)
 {
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
-    const uint32_t box[4] = {KCHUNK, TILE_W, TILE_H, 1};
+    const uint32_t box[4] = {(uint32_t)kc, TILE_W, TILE_H, 1};
     return encode_map(m, base, 4, dims, str, box);
 }
 // Parity view (py, px) of an NHWC tensor for stride-2 convs: element (y', x') = input (2y'+py, 2x'+px).
-static int map_nhwc_parity(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c, int py, int px)
+static int map_nhwc_parity(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c, int py, int px, int kc = KCHUNK)
 {
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)((w - px + 1) / 2), (uint64_t)((h - py + 1) / 2), (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)2 * c * 2, (uint64_t)2 * w * c * 2, (uint64_t)h * w * c * 2};
-    const uint32_t box[4] = {KCHUNK, TILE_W, TILE_H, 1};
+    const uint32_t box[4] = {(uint32_t)kc, TILE_W, TILE_H, 1};
     return encode_map(m, base + ((size_t)py * w + px) * c, 4, dims, str, box);
 }
 
@@ -770,6 +782,9 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     if (cl != 1 && cl != 2 && cl != 4) cl = 1;
     while (cl > 1 && (m_tiles0 % cl != 0 || (n_tile / cl) % 8 != 0 || n_tile / cl < 8)) cl >>= 1;
     if (d->halo) cl = 1;
+    // K elements per pipeline stage: 64 (128 B rows, SWIZZLE_128B) or 32 (64 B rows, SWIZZLE_64B: twice the stages)
+    int kc = KCHUNK;
+    { const char* e = getenv("LWB_KC"); if (e && atoi(e) == 32 && !d->rowk && !d->halo) { kc = 32; cl = 1; } }
 
     lwb_conv_plan* plan = new (std::nothrow) lwb_conv_plan();
     LWB_CHECK_ARG(plan, "out of host memory");
@@ -786,7 +801,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.n_tiles_n = d->cout / n_tile;
         p.out = out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
-        L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl;
+        L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl; L.kc = d->rowk ? KCHUNK : kc;
         p.stages = 64;      // clamped to Cfg::STAGES at launch
         const long total_super = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n / cl;
         const long max_clusters = sms / cl;
@@ -899,7 +914,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     LWB_CHECK_ARG(ntaps_w <= MAX_TAPS, "too many filter taps");
     const uint64_t wd[3] = {(uint64_t)cin_total, (uint64_t)d->cout, (uint64_t)ntaps_w};
     const uint64_t ws[2] = {(uint64_t)cin_total * 2, (uint64_t)d->cout * cin_total * 2};
-    const uint32_t wb[3] = {KCHUNK, (uint32_t)(n_tile / cl), 1};
+    const uint32_t wb[3] = {(uint32_t)kc, (uint32_t)(n_tile / cl), 1};
 
     if (d->transposed) {
         // ConvTranspose2d(k=3, s=2, p=1, output_padding=1): out[2i+a, 2j+b] gathers, per axis,
@@ -909,8 +924,8 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) {
             Launch& L = plan->launches[plan->num++];
             memset(&L.p, 0, sizeof(L.p));
-            if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0)) != LWB_OK) return fail(rc);
-            if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0)) != LWB_OK) return fail(rc);
+            if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0, kc)) != LWB_OK) return fail(rc);
+            if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0, kc)) != LWB_OK) return fail(rc);
             if ((rc = encode_map(&L.p.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
             if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
             const int ky_list[2][2] = {{1, -1}, {2, 0}}, d_list[2][2] = {{0, 0}, {0, 1}}, cnt[2] = {1, 2};
@@ -920,7 +935,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
                 L.p.tmap[t] = 0; L.p.wtap[t] = (short)(ky_list[a][i] * 3 + ky_list[b][j]);
                 t++;
             }
-            L.p.ntaps = t; L.p.chunks0 = d->cin0 / KCHUNK; L.p.chunks1 = 0;
+            L.p.ntaps = t; L.p.chunks0 = d->cin0 / kc; L.p.chunks1 = 0;
             L.p.oy_mul = 2; L.p.ox_mul = 2; L.p.oy_add = a; L.p.ox_add = b;
             finish(L, d->h_in, d->w_in);
         }
@@ -933,16 +948,16 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     Launch& L = plan->launches[plan->num++];
     memset(&L.p, 0, sizeof(L.p));
     if (d->stride == 1) {
-        if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0)) != LWB_OK) return fail(rc);
-        if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0)) != LWB_OK) return fail(rc);
+        if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0, kc)) != LWB_OK) return fail(rc);
+        if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0, kc)) != LWB_OK) return fail(rc);
         if (d->cin1) {
-            if ((rc = map_nhwc(&L.p.a_hi[1], x1_hi, d->n, d->h_in, d->w_in, d->cin1)) != LWB_OK) return fail(rc);
-            if (split && (rc = map_nhwc(&L.p.a_lo[1], x1_lo, d->n, d->h_in, d->w_in, d->cin1)) != LWB_OK) return fail(rc);
+            if ((rc = map_nhwc(&L.p.a_hi[1], x1_hi, d->n, d->h_in, d->w_in, d->cin1, kc)) != LWB_OK) return fail(rc);
+            if (split && (rc = map_nhwc(&L.p.a_lo[1], x1_lo, d->n, d->h_in, d->w_in, d->cin1, kc)) != LWB_OK) return fail(rc);
         }
     } else {
         for (int py = 0; py < 2; py++) for (int px = 0; px < 2; px++) {
-            if ((rc = map_nhwc_parity(&L.p.a_hi[py * 2 + px], x0_hi, d->n, d->h_in, d->w_in, d->cin0, py, px)) != LWB_OK) return fail(rc);
-            if (split && (rc = map_nhwc_parity(&L.p.a_lo[py * 2 + px], x0_lo, d->n, d->h_in, d->w_in, d->cin0, py, px)) != LWB_OK) return fail(rc);
+            if ((rc = map_nhwc_parity(&L.p.a_hi[py * 2 + px], x0_hi, d->n, d->h_in, d->w_in, d->cin0, py, px, kc)) != LWB_OK) return fail(rc);
+            if (split && (rc = map_nhwc_parity(&L.p.a_lo[py * 2 + px], x0_lo, d->n, d->h_in, d->w_in, d->cin0, py, px, kc)) != LWB_OK) return fail(rc);
         }
     }
     if ((rc = encode_map(&L.p.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
@@ -961,7 +976,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         L.p.wtap[t] = (short)t;
         t++;
     }
-    L.p.ntaps = t; L.p.chunks0 = d->cin0 / KCHUNK; L.p.chunks1 = d->cin1 / KCHUNK;
+    L.p.ntaps = t; L.p.chunks0 = d->cin0 / kc; L.p.chunks1 = d->cin1 / kc;
     L.p.oy_mul = 1; L.p.ox_mul = 1; L.p.oy_add = 0; L.p.ox_add = 0;
     finish(L, d->h_out, d->w_out);
     *plan_out = plan;
