@@ -315,8 +315,8 @@ def main():
         outs = imitator.inference_by_smpls(list(pinned[i % len(pinned)]), cam_strategy="smooth")
         assert len(outs) == B
     prof_flag, args.profile_range = args.profile_range, False
-    ms_e2e, _ = timed(step_e2e, args.steps if not args.no_extras else 1, max(args.warmup, 3) if not args.no_extras else 1)
-    e2e_fps = world * B * (args.steps if not args.no_extras else 1) / (ms_e2e * 1e-3)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    e2e_fps = world * B * args.steps / (ms_e2e * 1e-3)
     args.profile_range = prof_flag
 
     line = {"metric": "frames/sec @256x256 (per-frame inference hot path)", "value": fps, "unit": "frames/s",

@@ -768,7 +768,8 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     LWB_CHECK_ARG(!split || (x0_lo && w_lo), "split mode needs the lo operands");
     LWB_CHECK_ARG(d->n > 0 && d->h_in > 0 && d->w_in > 0 && d->cout > 0, "non-positive size");
     LWB_CHECK_ARG(d->cout % 16 == 0, "cout must be a multiple of 16");
-    const int n_tile = pick_n_tile(d->cout, split, d->n_tile);
+    int n_tile = pick_n_tile(d->cout, split, d->n_tile);
+    if (d->halo && split && n_tile == 256 && d->n_tile == 0) n_tile = 128;      // halo + split: the 256-wide weight ring does not fit
     LWB_CHECK_ARG(n_tile > 0 && d->cout % n_tile == 0, "no N tile divides cout");
 
     // Cluster size for weight-tile multicast (LWB_CLUSTER = 1 | 2 | 4, default 1): the CTAs of a cluster work on
