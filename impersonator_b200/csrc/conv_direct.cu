@@ -26,11 +26,10 @@ __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, c
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * HT_H, x0 = blockIdx.x * HT_W;
     const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;          // 8 x 16 threads, 4 px each along x
-    float acc[4][4];
+    // accumulators as packed pairs: Blackwell's FFMA2 (fma.rn.f32x2) retires two fp32 FMAs per issue slot
+    float2 acc[4][2];
 #pragma unroll
-    for (int p = 0; p < 4; p++)
-#pragma unroll
-        for (int o = 0; o < 4; o++) acc[p][o] = 0.f;
+    for (int p = 0; p < 4; p++) { acc[p][0] = make_float2(0.f, 0.f); acc[p][1] = make_float2(0.f, 0.f); }
 
     for (int c0 = 0; c0 < 64; c0 += HC) {
         __syncthreads();
@@ -64,13 +63,12 @@ __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, c
 #pragma unroll
                 for (int kx = 0; kx < 7; kx++) {
                     const float4 wv = *reinterpret_cast<const float4*>(&s_w[ky * 7 + kx][c][0]);
+                    const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
                     for (int p = 0; p < 4; p++) {
-                        const float v = in[p + kx];
-                        acc[p][0] = fmaf(v, wv.x, acc[p][0]);
-                        acc[p][1] = fmaf(v, wv.y, acc[p][1]);
-                        acc[p][2] = fmaf(v, wv.z, acc[p][2]);
-                        acc[p][3] = fmaf(v, wv.w, acc[p][3]);
+                        const float2 vv = make_float2(in[p + kx], in[p + kx]);
+                        acc[p][0] = __ffma2_rn(vv, w01, acc[p][0]);
+                        acc[p][1] = __ffma2_rn(vv, w23, acc[p][1]);
                     }
                 }
             }
@@ -83,7 +81,7 @@ __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, c
             const int xx = x0 + tx * 4 + p;
             if (xx < w)
                 *reinterpret_cast<float4*>(out + (((size_t)b * h + y) * w + xx) * 4) =
-                    make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+                    make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
         }
     }
 }

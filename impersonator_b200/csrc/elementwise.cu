@@ -164,7 +164,7 @@ struct NormActParams {
 struct TapRec { int o00, m; float w00, w01, w10, w11; };
 
 template <bool WARP>
-__global__ void __launch_bounds__(256) k_norm_act(NormActParams P)
+__global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
 {
     constexpr int R = 2;                                 // pixel rounds per thread
     const int groups = P.c >> 3;
