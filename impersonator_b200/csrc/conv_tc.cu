@@ -437,6 +437,7 @@ struct HaloParams {
     int a_plane_bytes;                // a_rows * pitch_bytes (one of hi / lo)
     int a_stage_bytes;                // a_plane_bytes * (SPLIT ? 2 : 1)
     int nb_stages;
+    int resident_b;                   // 1: the whole weight tensor (ntaps x nchunks tiles) stays in smem for the kernel's lifetime
     int bo_mode;                      // descriptor base_offset for a kx-shifted window: 0 (correct), 1 +kx, 2 -kx (LWB_HALO_BO, diagnostic only)
     float* out; int out_h, out_w, cout;
     int oy_mul, oy_add, ox_mul, ox_add;
@@ -525,9 +526,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
                 if (SPLIT) tma_load_4d(&P.a_lo[mi], sta + P.a_plane_bytes, bar_afull + sa, c0, x0, y0, img);
                 if (++sa == HALO_NA) { sa = 0; pa ^= 1; }
             };
+            if (P.resident_b && items > 0) {
+                // weights of every (chunk, tap) are fetched once; slot = chunk * ntaps + tap, barrier phase 0 forever
+                for (int ct = 0; ct < nchunks * ntaps; ct++) {
+                    uint8_t* stb = b_ring + ct * B_STAGE;
+                    mbar_expect_tx(bar_bfull + ct, (uint32_t)B_STAGE);
+                    tma_load_3d(&P.w_hi, stb, bar_bfull + ct, (ct / ntaps) * KCHUNK, 0, ct % ntaps);
+                    if (SPLIT) tma_load_3d(&P.w_lo, stb + B_BYTES, bar_bfull + ct, (ct / ntaps) * KCHUNK, 0, ct % ntaps);
+                }
+            }
             if (items > 0) issue_a(0);
             for (int item = 0; item < items; item++) {
                 if (item + 1 < items) issue_a(item + 1);
+                if (P.resident_b) continue;
                 const int tile = (int)blockIdx.x + (item / nchunks) * (int)gridDim.x;
                 const int chunk = item % nchunks;
                 const int n_idx = tile / m_tiles;
@@ -559,6 +570,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
                     const uint32_t a_hi = a_ring_u + sa * P.a_stage_bytes;
                     const uint32_t a_lo = a_hi + P.a_plane_bytes;
                     for (int tap = 0; tap < ntaps; tap++) {
+                        if (P.resident_b) { sb = chunk * ntaps + tap; pb = 0; }
                         mbar_wait(bar_bfull + sb, pb);
                         tc_fence_after();
                         const int ky = tap / P.kw, kx = tap - ky * P.kw;
@@ -576,8 +588,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
                                 umma_f16(d_tmem, make_desc_ex(a_lo + a_off + k * 32, (uint32_t)P.pitch_bytes, bo), db, idesc, 1u);
                             }
                         }
-                        umma_commit(bar_bempty + sb);
-                        if (++sb == nb) { sb = 0; pb ^= 1; }
+                        if (!P.resident_b) {
+                            umma_commit(bar_bempty + sb);
+                            if (++sb == nb) { sb = 0; pb ^= 1; }
+                        }
                     }
                     umma_commit(bar_aempty + sa);
                     if (++sa == HALO_NA) { sa = 0; pa ^= 1; }
@@ -864,6 +878,11 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         h.a_stage_bytes = h.a_plane_bytes * (split ? 2 : 1);
         const int fixed = 1024 + HALO_NA * h.a_stage_bytes + 256 + 4 * n_tile * 8;
         int nbs = (227 * 1024 - fixed) / b_stage;
+        {   // whole weight tensor resident when it fits (the 7x7 stem: 7 x 16 KB): then only activations stream
+            const int slots = (h.chunks0 + h.chunks1) * h.kh * h.kw;
+            h.resident_b = (d->cout == n_tile && slots <= HALO_MAX_NB && slots <= nbs) ? 1 : 0;
+            if (h.resident_b) nbs = slots;
+        }
         if (nbs > HALO_MAX_NB) nbs = HALO_MAX_NB;
         if (nbs < 2) { lwb::set_error("conv_halo: tile does not fit shared memory (n_tile %d, kh %d)", n_tile, d->kh); return fail(LWB_E_UNSUPPORTED); }
         h.nb_stages = nbs;
