@@ -45,3 +45,6 @@ bench("res 512->512 @32 B16 fast", 16, 512, 512, 32, 3, stats=True, split=False)
 bench("res 512->512 @32 B16 fast n128", 16, 512, 512, 32, 3, stats=True, split=False, n_tile=128)
 bench("res 512->512 @32 B16 split n256", 16, 512, 512, 32, 3, stats=True, n_tile=256)
 bench("skipper 64+64->64 @256 B16 fast", 16, 64, 64, 256, 3, stats=True, cin1=64, split=False)
+bench("stem rowk 8->64 @256 B16 halo(resident B)", 16, 8, 64, 256, 7, stats=True, halo=True, rowk=True)
+bench("stem rowk 8->64 @256 B16 halo fast", 16, 8, 64, 256, 7, stats=True, halo=True, rowk=True, split=False)
+bench("stem rowk 8->64 @256 B16 fast", 16, 8, 64, 256, 7, stats=True, halo=False, rowk=True, split=False)
