@@ -240,7 +240,7 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
             uint32_t r[CW];
             if (CW == 32) tmem_ld32(taddr + c * CW, r); else tmem_ld16(taddr + c * CW, r);
             tmem_ld_wait();
-            if (valid) {
+            if (valid && P.out) {
                 float4* o = reinterpret_cast<float4*>(optr + c * CW);
 #pragma unroll
                 for (int j = 0; j < CW / 4; j++)
@@ -814,7 +814,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.dom_h = dom_h; p.dom_w = dom_w;
         p.tiles_y = lwb::ceil_div(dom_h, TILE_H); p.tiles_x = lwb::ceil_div(dom_w, TILE_W);
         p.n_tiles_n = d->cout / n_tile;
-        p.out = out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
+        p.out = getenv("LWB_DEBUG_NOSTORE") ? nullptr : out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
         L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl; L.kc = d->rowk ? KCHUNK : kc;
         p.stages = 64;      // clamped to Cfg::STAGES at launch
