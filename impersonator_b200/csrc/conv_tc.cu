@@ -108,6 +108,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+// One lane of a CONVERGED warp.  Issuing TMA / tcgen05 under `if (elect_one())` (instead of `if (lane == 0)`)
+// keeps the surrounding control flow warp-uniform, so the compiler holds descriptors, coordinates and TMEM
+// addresses in uniform registers; under a lane-id branch every UTCHMMA/UTMALDG operand goes through an
+// ELECT + R2UR.BROADCAST waterfall loop (~12 extra dependent instructions per MMA, measured issue-bound).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -320,13 +329,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     constexpr int B_SLICE = N_TILE / CL;         // weight rows this CTA fetches (and multicasts) per stage
 
     if (warp == 0) {
-        // ================================ TMA producer =================================
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" :: "l"(&P.a_hi[0]) : "memory");
-            asm volatile("prefetch.tensormap [%0];" :: "l"(&P.w_hi) : "memory");
-            if (SPLIT) {
-                asm volatile("prefetch.tensormap [%0];" :: "l"(&P.a_lo[0]) : "memory");
-                asm volatile("prefetch.tensormap [%0];" :: "l"(&P.w_lo) : "memory");
+        // ================================ TMA producer (whole warp, one elected lane issues) ==========
+        {
+            if (elect_one()) {
+                asm volatile("prefetch.tensormap [%0];" :: "l"(&P.a_hi[0]) : "memory");
+                asm volatile("prefetch.tensormap [%0];" :: "l"(&P.w_hi) : "memory");
+                if (SPLIT) {
+                    asm volatile("prefetch.tensormap [%0];" :: "l"(&P.a_lo[0]) : "memory");
+                    asm volatile("prefetch.tensormap [%0];" :: "l"(&P.w_lo) : "memory");
+                }
             }
             int stage = 0; uint32_t phase = 0;
             for (int sup = sch.first; sup < sch.total; sup += sch.step) {
@@ -338,32 +349,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                 for (int s = 0; s < ksteps; s++) {
                     mbar_wait(bar_empty + stage, phase ^ 1);
                     uint8_t* st = smem + stage * C::STAGE_BYTES;
-                    mbar_expect_tx(bar_full + stage, (uint32_t)C::STAGE_BYTES);
                     const int tap = s / nchunks, chunk = s % nchunks;
                     const bool second = chunk >= P.chunks0;
                     const int mi = second ? 1 : P.tmap[tap];
                     const int c0 = (second ? chunk - P.chunks0 : chunk) * KC;
                     const int xx = x0 + P.dx[tap], yy = y0 + P.dy[tap];
-                    tma_load_4d(&P.a_hi[mi], st, bar_full + stage, c0, xx, yy, img);
-                    if (SPLIT) tma_load_4d(&P.a_lo[mi], st + C::A_TILE, bar_full + stage, c0, xx, yy, img);
+                    const int wt = P.wtap[tap];
                     uint8_t* sb = st + C::A_TILE * (SPLIT ? 2 : 1);
-                    if (CL == 1) {
-                        tma_load_3d(&P.w_hi, sb, bar_full + stage, chunk * KC, n_idx * N_TILE, P.wtap[tap]);
-                        if (SPLIT) tma_load_3d(&P.w_lo, sb + C::B_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE, P.wtap[tap]);
-                    } else {
-                        const int r0 = sch.rank * B_SLICE;
-                        tma_load_3d_mc(&P.w_hi, sb + r0 * C::ROW_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE + r0, P.wtap[tap], kMask);
-                        if (SPLIT) tma_load_3d_mc(&P.w_lo, sb + C::B_BYTES + r0 * C::ROW_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE + r0, P.wtap[tap], kMask);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + stage, (uint32_t)C::STAGE_BYTES);
+                        tma_load_4d(&P.a_hi[mi], st, bar_full + stage, c0, xx, yy, img);
+                        if (SPLIT) tma_load_4d(&P.a_lo[mi], st + C::A_TILE, bar_full + stage, c0, xx, yy, img);
+                        if (CL == 1) {
+                            tma_load_3d(&P.w_hi, sb, bar_full + stage, chunk * KC, n_idx * N_TILE, wt);
+                            if (SPLIT) tma_load_3d(&P.w_lo, sb + C::B_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE, wt);
+                        } else {
+                            const int r0 = sch.rank * B_SLICE;
+                            tma_load_3d_mc(&P.w_hi, sb + r0 * C::ROW_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE + r0, wt, kMask);
+                            if (SPLIT) tma_load_3d_mc(&P.w_lo, sb + C::B_BYTES + r0 * C::ROW_BYTES, bar_full + stage, chunk * KC, n_idx * N_TILE + r0, wt, kMask);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ===================================
-        if (lane == 0) {
+        // ================================ MMA issuer (whole warp, one elected lane issues) ============
+        {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t smem_base = smem_u32(smem);
             int stage = 0; uint32_t phase = 0;
             int abuf = 0; uint32_t aphase = 0;
             for (int sup = sch.first; sup < sch.total; sup += sch.step) {
@@ -373,24 +389,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                 for (int s = 0; s < ksteps; s++) {
                     mbar_wait(bar_full + stage, phase);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t a_hi = smem_base + stage * C::STAGE_BYTES;
                     const uint32_t a_lo = a_hi + C::A_TILE;
                     const uint32_t b_hi = a_hi + C::A_TILE * (SPLIT ? 2 : 1);
                     const uint32_t b_lo = b_hi + C::B_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < KC / 16; k++) {
-                        const uint64_t da = make_desc_k<KC>(a_hi + k * 32), db = make_desc_k<KC>(b_hi + k * 32);
-                        umma_f16(d_tmem, da, db, idesc, (s > 0 || k > 0) ? 1u : 0u);
-                        if (SPLIT) {
-                            umma_f16(d_tmem, da, make_desc_k<KC>(b_lo + k * 32), idesc, 1u);
-                            umma_f16(d_tmem, make_desc_k<KC>(a_lo + k * 32), db, idesc, 1u);
+                        for (int k = 0; k < KC / 16; k++) {
+                            const uint64_t da = make_desc_k<KC>(a_hi + k * 32), db = make_desc_k<KC>(b_hi + k * 32);
+                            umma_f16(d_tmem, da, db, idesc, (s > 0 || k > 0) ? 1u : 0u);
+                            if (SPLIT) {
+                                umma_f16(d_tmem, da, make_desc_k<KC>(b_lo + k * 32), idesc, 1u);
+                                umma_f16(d_tmem, make_desc_k<KC>(a_lo + k * 32), db, idesc, 1u);
+                            }
                         }
+                        // smem slot free (in every CTA of the cluster) once these MMAs retire
+                        if (CL == 1) umma_commit(bar_empty + stage); else umma_commit_mc(bar_empty + stage, kMask);
                     }
-                    // smem slot free (in every CTA of the cluster) once these MMAs retire
-                    if (CL == 1) umma_commit(bar_empty + stage); else umma_commit_mc(bar_empty + stage, kMask);
+                    __syncwarp();
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + abuf);                      // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(bar_tfull + abuf);     // accumulator complete -> epilogue
+                __syncwarp();
                 if (++abuf == 2) { abuf = 0; aphase ^= 1; }
             }
         }
