@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
         // Work items = (tile, chunk) in execution order.  The activation halo of item i+1 is requested
         // BEFORE the weight taps of item i are streamed, so the big A transfer has a whole chunk of MMA
         // time to land (the weight ring alone would only let it start 2-4 taps before it is needed).
-        if (lane == 0) {
+        {
             int sa = 0; uint32_t pa = 0;
             int sb = 0; uint32_t pb = 0;
             const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -541,18 +541,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
                 const int c0 = (second ? chunk - P.chunks0 : chunk) * KCHUNK;
                 mbar_wait(bar_aempty + sa, pa ^ 1);
                 uint8_t* sta = a_ring + sa * P.a_stage_bytes;
-                mbar_expect_tx(bar_afull + sa, (uint32_t)P.a_stage_bytes);
-                tma_load_4d(&P.a_hi[mi], sta, bar_afull + sa, c0, x0, y0, img);
-                if (SPLIT) tma_load_4d(&P.a_lo[mi], sta + P.a_plane_bytes, bar_afull + sa, c0, x0, y0, img);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_afull + sa, (uint32_t)P.a_stage_bytes);
+                    tma_load_4d(&P.a_hi[mi], sta, bar_afull + sa, c0, x0, y0, img);
+                    if (SPLIT) tma_load_4d(&P.a_lo[mi], sta + P.a_plane_bytes, bar_afull + sa, c0, x0, y0, img);
+                }
+                __syncwarp();
                 if (++sa == HALO_NA) { sa = 0; pa ^= 1; }
             };
             if (P.resident_b && items > 0) {
                 // weights of every (chunk, tap) are fetched once; slot = chunk * ntaps + tap, barrier phase 0 forever
                 for (int ct = 0; ct < nchunks * ntaps; ct++) {
                     uint8_t* stb = b_ring + ct * B_STAGE;
-                    mbar_expect_tx(bar_bfull + ct, (uint32_t)B_STAGE);
-                    tma_load_3d(&P.w_hi, stb, bar_bfull + ct, (ct / ntaps) * KCHUNK, 0, ct % ntaps);
-                    if (SPLIT) tma_load_3d(&P.w_lo, stb + B_BYTES, bar_bfull + ct, (ct / ntaps) * KCHUNK, 0, ct % ntaps);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_bfull + ct, (uint32_t)B_STAGE);
+                        tma_load_3d(&P.w_hi, stb, bar_bfull + ct, (ct / ntaps) * KCHUNK, 0, ct % ntaps);
+                        if (SPLIT) tma_load_3d(&P.w_lo, stb + B_BYTES, bar_bfull + ct, (ct / ntaps) * KCHUNK, 0, ct % ntaps);
+                    }
+                    __syncwarp();
                 }
             }
             if (items > 0) issue_a(0);
@@ -565,16 +571,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
                 for (int tap = 0; tap < ntaps; tap++) {
                     mbar_wait(bar_bempty + sb, pb ^ 1);
                     uint8_t* stb = b_ring + sb * B_STAGE;
-                    mbar_expect_tx(bar_bfull + sb, (uint32_t)B_STAGE);
-                    tma_load_3d(&P.w_hi, stb, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
-                    if (SPLIT) tma_load_3d(&P.w_lo, stb + B_BYTES, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_bfull + sb, (uint32_t)B_STAGE);
+                        tma_load_3d(&P.w_hi, stb, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
+                        if (SPLIT) tma_load_3d(&P.w_lo, stb + B_BYTES, bar_bfull + sb, chunk * KCHUNK, n_idx * N_TILE, tap);
+                    }
+                    __syncwarp();
                     if (++sb == nb) { sb = 0; pb ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ===================================
-        if (lane == 0) {
+        // ================================ MMA issuer (whole warp, elected lane issues) ==
+        {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int sa = 0; uint32_t pa = 0;
             int sb = 0; uint32_t pb = 0;
@@ -598,25 +607,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
                         const uint32_t bo = P.bo_mode == 1 ? (uint32_t)kx : (P.bo_mode == 2 ? (uint32_t)((8 - kx) & 7) : 0u);
                         const uint32_t b_hi = b_ring_u + sb * B_STAGE;
                         const uint32_t b_lo = b_hi + B_BYTES;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < KCHUNK / 16; k++) {
-                            const uint64_t da = make_desc_ex(a_hi + a_off + k * 32, (uint32_t)P.pitch_bytes, bo);
-                            const uint64_t db = make_desc(b_hi + k * 32);
-                            umma_f16(d_tmem, da, db, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                            if (SPLIT) {
-                                umma_f16(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
-                                umma_f16(d_tmem, make_desc_ex(a_lo + a_off + k * 32, (uint32_t)P.pitch_bytes, bo), db, idesc, 1u);
+                            for (int k = 0; k < KCHUNK / 16; k++) {
+                                const uint64_t da = make_desc_ex(a_hi + a_off + k * 32, (uint32_t)P.pitch_bytes, bo);
+                                const uint64_t db = make_desc(b_hi + k * 32);
+                                umma_f16(d_tmem, da, db, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                                if (SPLIT) {
+                                    umma_f16(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
+                                    umma_f16(d_tmem, make_desc_ex(a_lo + a_off + k * 32, (uint32_t)P.pitch_bytes, bo), db, idesc, 1u);
+                                }
                             }
+                            if (!P.resident_b) umma_commit(bar_bempty + sb);
                         }
-                        if (!P.resident_b) {
-                            umma_commit(bar_bempty + sb);
-                            if (++sb == nb) { sb = 0; pb ^= 1; }
-                        }
+                        __syncwarp();
+                        if (!P.resident_b) { if (++sb == nb) { sb = 0; pb ^= 1; } }
                     }
-                    umma_commit(bar_aempty + sa);
+                    if (elect_one()) umma_commit(bar_aempty + sa);
+                    __syncwarp();
                     if (++sa == HALO_NA) { sa = 0; pa ^= 1; }
                 }
-                umma_commit(bar_tfull + abuf);
+                if (elect_one()) umma_commit(bar_tfull + abuf);
+                __syncwarp();
                 if (++abuf == 2) { abuf = 0; aphase ^= 1; }
             }
         }

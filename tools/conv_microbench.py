@@ -36,7 +36,7 @@ def bench(name, n, cin, cout, h, k, stats=True, halo=False, n_tile=0, split=True
 
 
 for stats in (True,):
-    for halo in (False,):
+    for halo in (False, True):
         bench("stem rowk 8->64 @256 B16", 16, 8, 64, 256, 7, stats=stats, halo=halo, rowk=True)
         bench("skipper 64+64->64 @256 B16", 16, 64, 64, 256, 3, stats=stats, halo=halo, cin1=64)
         bench("skipper 128+128->128 @128 B16", 16, 128, 128, 128, 3, stats=stats, halo=halo, cin1=128)
