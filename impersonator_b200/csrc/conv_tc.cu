@@ -245,7 +245,7 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * N_TILE);
         constexpr int CW = N_TILE >= 32 ? 32 : 16;
 #pragma unroll 1
-        for (int c = 0; c < N_TILE / CW; c++) {
+        for (int c = 0; c < (P.oy_mul < 0 ? 0 : N_TILE / CW); c++) {      // oy_mul < 0: debug, skip the epilogue body
             uint32_t r[CW];
             if (CW == 32) tmem_ld32(taddr + c * CW, r); else tmem_ld16(taddr + c * CW, r);
             tmem_ld_wait();
@@ -846,6 +846,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.dom_h = dom_h; p.dom_w = dom_w;
         p.tiles_y = lwb::ceil_div(dom_h, TILE_H); p.tiles_x = lwb::ceil_div(dom_w, TILE_W);
         p.n_tiles_n = d->cout / n_tile;
+        if (getenv("LWB_DEBUG_NOEPI")) { p.oy_mul = -1; }
         p.out = getenv("LWB_DEBUG_NOSTORE") ? nullptr : out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
         L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl; L.kc = d->rowk ? KCHUNK : kc;
