@@ -68,13 +68,17 @@ struct Cfg {
     static constexpr int STAGE_BYTES = (A_TILE + B_BYTES) * (SPLIT ? 2 : 1);
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int TMEM_COLS = (2 * N_TILE <= 32) ? 32 : (2 * N_TILE <= 64) ? 64 : (2 * N_TILE <= 128) ? 128
-                                   : (2 * N_TILE <= 256) ? 256 : 512;
+    // Split mode issues three dependent-looking MMAs per K step; when TMEM has room each product gets its OWN
+    // accumulator (summed in the epilogue) so that consecutive MMAs do not serialise on one accumulator.
+    static constexpr int NACC = (SPLIT && 6 * N_TILE <= 512) ? 3 : 1;
+    static constexpr int ACC_COLS = 2 * NACC * N_TILE;
+    static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128
+                                   : (ACC_COLS <= 256) ? 256 : 512;
     static constexpr int BAR_BYTES = 256;
     static constexpr int STATS_BYTES = 4 * N_TILE * 2 * 4;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + STATS_BYTES;
     static_assert(STAGES >= 2, "need at least two pipeline stages");
-    static_assert(2 * N_TILE <= 512, "accumulator double buffer exceeds TMEM");
+    static_assert(ACC_COLS <= 512, "accumulator double buffer exceeds TMEM");
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -222,7 +226,7 @@ __device__ __forceinline__ float warp_col_sums(float* v, unsigned lane) {
 
 
 // Epilogue warps (4): TMEM accumulator -> fp32 NHWC global + InstanceNorm partial statistics.
-template <int N_TILE, class PT>
+template <int N_TILE, int NACC, class PT>
 __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned lane, const Sched& sch,
                                               uint32_t tmem_base, uint64_t* bar_tfull, uint64_t* bar_tempty, float2* s_stats)
 {
@@ -242,12 +246,21 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
                     + (size_t)n_idx * N_TILE;
         mbar_wait(bar_tfull + abuf, aphase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * N_TILE);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * NACC * N_TILE);
         constexpr int CW = N_TILE >= 32 ? 32 : 16;
 #pragma unroll 1
         for (int c = 0; c < (P.oy_mul < 0 ? 0 : N_TILE / CW); c++) {      // oy_mul < 0: debug, skip the epilogue body
             uint32_t r[CW];
             if (CW == 32) tmem_ld32(taddr + c * CW, r); else tmem_ld16(taddr + c * CW, r);
+            if (NACC > 1) {
+                uint32_t r1[CW], r2[CW];
+                if (CW == 32) { tmem_ld32(taddr + N_TILE + c * CW, r1); tmem_ld32(taddr + 2 * N_TILE + c * CW, r2); }
+                else          { tmem_ld16(taddr + N_TILE + c * CW, r1); tmem_ld16(taddr + 2 * N_TILE + c * CW, r2); }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CW; j++)
+                    r[j] = __float_as_uint(__uint_as_float(r[j]) + (__uint_as_float(r1[j]) + __uint_as_float(r2[j])));
+            }
             tmem_ld_wait();
             if (valid && P.out) {
                 float4* o = reinterpret_cast<float4*>(optr + c * CW);
@@ -385,7 +398,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
             for (int sup = sch.first; sup < sch.total; sup += sch.step) {
                 mbar_wait(bar_tempty + abuf, aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * N_TILE);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * C::NACC * N_TILE);
                 for (int s = 0; s < ksteps; s++) {
                     mbar_wait(bar_full + stage, phase);
                     tc_fence_after();
@@ -397,10 +410,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
 #pragma unroll
                         for (int k = 0; k < KC / 16; k++) {
                             const uint64_t da = make_desc_k<KC>(a_hi + k * 32), db = make_desc_k<KC>(b_hi + k * 32);
-                            umma_f16(d_tmem, da, db, idesc, (s > 0 || k > 0) ? 1u : 0u);
+                            const uint32_t first = (s > 0 || k > 0) ? 1u : 0u;
+                            umma_f16(d_tmem, da, db, idesc, first);
                             if (SPLIT) {
-                                umma_f16(d_tmem, da, make_desc_k<KC>(b_lo + k * 32), idesc, 1u);
-                                umma_f16(d_tmem, make_desc_k<KC>(a_lo + k * 32), db, idesc, 1u);
+                                constexpr uint32_t A1 = C::NACC > 1 ? N_TILE : 0, A2 = C::NACC > 1 ? 2 * N_TILE : 0;
+                                umma_f16(d_tmem + A1, da, make_desc_k<KC>(b_lo + k * 32), idesc, C::NACC > 1 ? first : 1u);
+                                umma_f16(d_tmem + A2, make_desc_k<KC>(a_lo + k * 32), db, idesc, C::NACC > 1 ? first : 1u);
                             }
                         }
                         // smem slot free (in every CTA of the cluster) once these MMAs retire
@@ -416,7 +431,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
         }
     } else {
         // ================================ epilogue (4 warps) ===========================
-        epilogue_loop<N_TILE>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
+        epilogue_loop<N_TILE, C::NACC>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
     }
 
     tc_fence_before();
@@ -634,7 +649,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_halo(const __grid_const
         }
     } else {
         const Sched sch = make_sched(m_tiles, P.n_tiles_n, 1);
-        epilogue_loop<N_TILE>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
+        epilogue_loop<N_TILE, 1>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
     }
 
     tc_fence_before();
