@@ -68,9 +68,10 @@ struct Cfg {
     static constexpr int STAGE_BYTES = (A_TILE + B_BYTES) * (SPLIT ? 2 : 1);
     static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    // Split mode issues three dependent-looking MMAs per K step; when TMEM has room each product gets its OWN
-    // accumulator (summed in the epilogue) so that consecutive MMAs do not serialise on one accumulator.
-    static constexpr int NACC = (SPLIT && 6 * N_TILE <= 512) ? 3 : 1;
+    // NACC = 3 gives each of the three split products its own TMEM accumulator (summed in the epilogue).  Measured
+    // on B200: no gain (0.528 vs 0.518 ms on the 64-channel skipper) -- the ~50-cycle per-instruction overhead of a
+    // tcgen05.mma is not an accumulator dependency -- so one accumulator is used.  (Kept: 6*N_TILE <= 512 allows 3.)
+    static constexpr int NACC = 1;
     static constexpr int ACC_COLS = 2 * NACC * N_TILE;
     static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128
                                    : (ACC_COLS <= 256) ? 256 : 512;
