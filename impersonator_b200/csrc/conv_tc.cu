@@ -226,8 +226,17 @@ __device__ __forceinline__ float warp_col_sums(float* v, unsigned lane) {
 }
 
 
+__device__ __forceinline__ uint32_t mapa_cta0(uint32_t local_addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+
 // Epilogue warps (4): TMEM accumulator -> fp32 NHWC global + InstanceNorm partial statistics.
-template <int N_TILE, int NACC, class PT>
+template <int N_TILE, int NACC, bool TWO_SM = false, class PT>
 __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned lane, const Sched& sch,
                                               uint32_t tmem_base, uint64_t* bar_tfull, uint64_t* bar_tempty, float2* s_stats)
 {
@@ -282,7 +291,10 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
         // all TMEM reads of this buffer are complete: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + abuf);
+        if (lane == 0) {
+            if (TWO_SM) mbar_arrive_cluster(mapa_cta0(smem_u32(bar_tempty + abuf)));     // the leader's barrier collects both CTAs
+            else        mbar_arrive(bar_tempty + abuf);
+        }
         if (P.stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int col = et; col < N_TILE; col += 128) {
@@ -442,6 +454,171 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================
+// 2-CTA variant (tcgen05 cta_group::2): a CTA pair (cluster 2x1x1, one TPC) computes TWO M tiles of the
+// same N tile with ONE M256 x N x K16 instruction issued by the leader CTA.  Each CTA stages its own
+// activation tile and only HALF of the weight tile (N/2 rows); the tensor cores of the pair read the
+// other half from the peer's shared memory.  Per CTA and stage this halves the weight bytes written by
+// TMA and read by the MMAs -- the kernel is shared-memory-bandwidth bound -- and
+// frees shared memory for a third stage at N = 256 (64 KB instead of 96 KB per stage).
+//   full[s]   lives in the leader; both CTAs' TMA loads (cta_group::2) complete their bytes on it
+//   empty[s]  one per CTA; the leader's commit is multicast to both
+//   tfull[b]  one per CTA (multicast commit); tempty[b] lives in the leader, 4 warps x 2 CTAs arrive on it
+// =====================================================================================================
+template <int N_TILE, bool SPLIT>
+struct Cfg2 {
+    static constexpr int B_HALF = (N_TILE / 2) * 128;
+    static constexpr int STAGE_BYTES = (A_BYTES + B_HALF) * (SPLIT ? 2 : 1);       // per CTA
+    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int TMEM_COLS = Cfg<N_TILE, SPLIT>::TMEM_COLS;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + 4 * N_TILE * 2 * 4;
+};
+
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, void* dst, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, void* dst, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+template <int N_TILE, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2(const __grid_constant__ ConvParams P)
+{
+    using C = Cfg2<N_TILE, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* bar_empty = bar_full + C::STAGES;
+    uint64_t* bar_tfull = bar_empty + C::STAGES;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    float2* s_stats = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < C::STAGES; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+            for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + b, 1); mbar_init(bar_tempty + b, 8); }
+            fence_barrier_init();
+            fence_proxy_async();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nchunks = P.chunks0 + P.chunks1;
+    const int ksteps = P.ntaps * nchunks;
+    const int m_tiles = P.n_img * P.tiles_y * P.tiles_x;
+    const Sched sch = make_sched(m_tiles, P.n_tiles_n, 2);
+
+    if (warp == 0) {
+        // ================================ TMA producer (both CTAs) ======================
+        int stage = 0; uint32_t phase = 0;
+        for (int sup = sch.first; sup < sch.total; sup += sch.step) {
+            int n_idx, m_idx;
+            sch.decode(sup, n_idx, m_idx);
+            const int img = m_idx / (P.tiles_y * P.tiles_x);
+            const int rem = m_idx % (P.tiles_y * P.tiles_x);
+            const int y0 = (rem / P.tiles_x) * TILE_H, x0 = (rem % P.tiles_x) * TILE_W;
+            for (int s = 0; s < ksteps; s++) {
+                mbar_wait(bar_empty + stage, phase ^ 1);
+                uint8_t* st = smem + stage * C::STAGE_BYTES;
+                const int tap = s / nchunks, chunk = s % nchunks;
+                const bool second = chunk >= P.chunks0;
+                const int mi = second ? 1 : P.tmap[tap];
+                const int c0 = (second ? chunk - P.chunks0 : chunk) * KCHUNK;
+                const int xx = x0 + P.dx[tap], yy = y0 + P.dy[tap];
+                const int wt = P.wtap[tap];
+                const int nrow = n_idx * N_TILE + (int)rank * (N_TILE / 2);
+                uint8_t* sb = st + A_BYTES * (SPLIT ? 2 : 1);
+                const uint32_t fullc = mapa_cta0(smem_u32(bar_full + stage));       // the leader's barrier
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(bar_full + stage, 2u * (uint32_t)C::STAGE_BYTES);   // both CTAs' bytes
+                    tma_load_4d_2sm(&P.a_hi[mi], st, fullc, c0, xx, yy, img);
+                    if (SPLIT) tma_load_4d_2sm(&P.a_lo[mi], st + A_BYTES, fullc, c0, xx, yy, img);
+                    tma_load_3d_2sm(&P.w_hi, sb, fullc, chunk * KCHUNK, nrow, wt);
+                    if (SPLIT) tma_load_3d_2sm(&P.w_lo, sb + C::B_HALF, fullc, chunk * KCHUNK, nrow, wt);
+                }
+                __syncwarp();
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ==================
+        if (leader) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t smem_base = smem_u32(smem);
+            int stage = 0; uint32_t phase = 0;
+            int abuf = 0; uint32_t aphase = 0;
+            for (int sup = sch.first; sup < sch.total; sup += sch.step) {
+                mbar_wait(bar_tempty + abuf, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * N_TILE);
+                for (int s = 0; s < ksteps; s++) {
+                    mbar_wait(bar_full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_base + stage * C::STAGE_BYTES;
+                    const uint32_t a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + A_BYTES * (SPLIT ? 2 : 1);
+                    const uint32_t b_lo = b_hi + C::B_HALF;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < KCHUNK / 16; k++) {
+                            const uint64_t da = make_desc(a_hi + k * 32), db = make_desc(b_hi + k * 32);
+                            umma_f16_2sm(d_tmem, da, db, idesc, (s > 0 || k > 0) ? 1u : 0u);
+                            if (SPLIT) {
+                                umma_f16_2sm(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
+                                umma_f16_2sm(d_tmem, make_desc(a_lo + k * 32), db, idesc, 1u);
+                            }
+                        }
+                        umma_commit_2sm(bar_empty + stage, 3);          // stage free in BOTH CTAs
+                    }
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (elect_one()) umma_commit_2sm(bar_tfull + abuf, 3);  // accumulators complete in both CTAs
+                __syncwarp();
+                if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue (both CTAs, own TMEM rows) ===========
+        epilogue_loop<N_TILE, 1, true>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
     }
 }
 
@@ -711,6 +888,7 @@ struct Launch {
     bool split;
     int cl;
     int kc;
+    bool two_sm;
     int grid;
 };
 
@@ -755,8 +933,31 @@ int launch_cl(const Launch& L, cudaStream_t st)
 }
 
 template <int N_TILE, bool SPLIT>
+int launch_2sm(const Launch& L, cudaStream_t st)
+{
+    using C = Cfg2<N_TILE, SPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc2<N_TILE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    LWB_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tc2<N_TILE, SPLIT>, L.p));
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+template <int N_TILE, bool SPLIT>
 int launch_one(const Launch& L, cudaStream_t st)
 {
+    if (L.two_sm) {
+        if constexpr (N_TILE >= 64) return launch_2sm<N_TILE, SPLIT>(L, st);
+    }
     if (L.kc == 32) return launch_cl<N_TILE, SPLIT, 1, 32>(L, st);
     if (L.cl == 2) return launch_cl<N_TILE, SPLIT, 2, 64>(L, st);
     if (L.cl == 4 && N_TILE >= 32) return launch_cl<N_TILE, SPLIT, (N_TILE >= 32 ? 4 : 1), 64>(L, st);
@@ -834,6 +1035,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     if (d->halo && split && n_tile == 256 && d->n_tile == 0) n_tile = 128;      // halo + split: the 256-wide weight ring does not fit
     LWB_CHECK_ARG(n_tile > 0 && d->cout % n_tile == 0, "no N tile divides cout");
 
+    const int sms = lwb::sm_count();
     // Cluster size for weight-tile multicast (LWB_CLUSTER = 1 | 2 | 4, default 1): the CTAs of a cluster work on
     // consecutive M tiles of the same N tile, each fetches 1/CL of the weight tile and multicasts it.
     // Measured on B200 (tools/conv_microbench.py): CL=2 is within 2% of CL=1 on every layer, CL=4 is slower --
@@ -845,16 +1047,20 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     if (cl != 1 && cl != 2 && cl != 4) cl = 1;
     while (cl > 1 && (m_tiles0 % cl != 0 || (n_tile / cl) % 8 != 0 || n_tile / cl < 8)) cl >>= 1;
     if (d->halo) cl = 1;
+    // 2-CTA MMA (cta_group::2, LWB_2SM=0 disables): pairs of M tiles share one weight tile, half of it per CTA
+    bool two_sm = false;
+    { const char* e = getenv("LWB_2SM"); const int want = e ? atoi(e) : 1;
+      two_sm = want && !d->halo && !d->rowk && n_tile >= 64 && (m_tiles0 % 2 == 0) && sms >= 2; }
+    if (two_sm) cl = 2;
     // K elements per pipeline stage: 64 (128 B rows, SWIZZLE_128B) or 32 (64 B rows, SWIZZLE_64B: twice the stages)
     int kc = KCHUNK;
-    { const char* e = getenv("LWB_KC"); if (e && atoi(e) == 32 && !d->rowk && !d->halo) { kc = 32; cl = 1; } }
+    { const char* e = getenv("LWB_KC"); if (e && atoi(e) == 32 && !d->rowk && !d->halo) { kc = 32; cl = 1; two_sm = false; } }
 
     lwb_conv_plan* plan = new (std::nothrow) lwb_conv_plan();
     LWB_CHECK_ARG(plan, "out of host memory");
     plan->num = 0;
     int rc = LWB_OK;
     auto fail = [&](int code) { delete plan; return code; };
-    const int sms = lwb::sm_count();
 
     auto finish = [&](Launch& L, int dom_h, int dom_w) {
         ConvParams& p = L.p;
@@ -866,6 +1072,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.out = getenv("LWB_DEBUG_NOSTORE") ? nullptr : out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
         L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl; L.kc = d->rowk ? KCHUNK : kc;
+        L.two_sm = two_sm && !d->rowk;
         p.stages = 64;      // clamped to Cfg::STAGES at launch
         const long total_super = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n / cl;
         const long max_clusters = sms / cl;
@@ -942,7 +1149,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         h.out = out_raw; h.out_h = d->h_out; h.out_w = d->w_out; h.cout = d->cout;
         h.oy_mul = 1; h.ox_mul = 1; h.oy_add = 0; h.ox_add = 0;
         h.stats = stats;
-        L.n_tile = n_tile; L.split = split; L.cl = 1;
+        L.n_tile = n_tile; L.split = split; L.cl = 1; L.two_sm = false;
         const long total = (long)h.n_img * h.tiles_y * h.tiles_x * h.n_tiles_n;
         L.grid = (int)(total < sms ? total : sms);
         *plan_out = plan;
