@@ -12,37 +12,37 @@ namespace {
 // Channels are processed 8 at a time: halo tile (22 x 38 px x 8 ch) + weights (49 x 8 x 4) in smem.
 // Per (ky, c-chunk): 10 input float4 pairs feed 4 px x 7 kx x 8 c x 4 co = 896 FMAs.
 // ------------------------------------------------------------------------------------------
-constexpr int HT_H = 16, HT_W = 32, HC = 8, HALO = 3;
-constexpr int HP_H = HT_H + 2 * HALO, HP_W = HT_W + 2 * HALO;       // 22 x 38 halo tile
-constexpr int HP_WP = 40;                                           // padded row pitch (floats), 16B aligned
+constexpr int HT_H = 16, HT_W = 64, HC = 4, HALO = 3, HPX = 8;       // 8 px per thread along x
+constexpr int HP_H = HT_H + 2 * HALO, HP_W = HT_W + 2 * HALO;       // 22 x 70 halo tile
+constexpr int HP_WP = 72;                                           // padded row pitch (floats), 16B aligned
 
 __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, const float* __restrict__ w4,
                                                   int n, int h, int w, float* __restrict__ out)
 {
-    // s_in[row][channel][x]: a thread's 10 consecutive x of one channel are 3 aligned float4 loads and
-    // the 8 threads of a quarter-warp read 128 contiguous bytes -> no bank conflicts.
-    __shared__ __align__(16) float s_in[HP_H][HC][HP_WP];           // 28160 B
-    __shared__ __align__(16) float s_w[49][HC][4];                  //  6272 B
+    // s_in[row][channel][x]: a thread's 16 consecutive x of one channel are 4 aligned float4 loads (14 used for
+    // 8 outputs x 7 taps).
+    __shared__ __align__(16) float s_in[HP_H][HC][HP_WP];           // 25344 B
+    __shared__ __align__(16) float s_w[49][HC][4];                  //  3136 B
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * HT_H, x0 = blockIdx.x * HT_W;
-    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;          // 8 x 16 threads, 4 px each along x
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;          // 8 x 16 threads, 8 px each along x
     // accumulators as packed pairs: Blackwell's FFMA2 (fma.rn.f32x2) retires two fp32 FMAs per issue slot
-    float2 acc[4][2];
+    float2 acc[HPX][2];
 #pragma unroll
-    for (int p = 0; p < 4; p++) { acc[p][0] = make_float2(0.f, 0.f); acc[p][1] = make_float2(0.f, 0.f); }
+    for (int p = 0; p < HPX; p++) { acc[p][0] = make_float2(0.f, 0.f); acc[p][1] = make_float2(0.f, 0.f); }
 
     for (int c0 = 0; c0 < 64; c0 += HC) {
         __syncthreads();
-        // fill: consecutive threads take consecutive x of one (row, channel-quad) -> coalesced 16B global
-        // reads (stride 256B between pixels) and conflict-free scalar smem stores
-        for (int i = threadIdx.x; i < HP_H * 2 * HP_WP; i += 128) {
-            const int px = i % HP_WP, half = (i / HP_WP) & 1, py = i / (2 * HP_WP);
+        // fill: consecutive threads take consecutive x of one row -> 16B global reads (stride 256B between pixels)
+        // and conflict-free scalar smem stores
+        for (int i = threadIdx.x; i < HP_H * HP_WP; i += 128) {
+            const int px = i % HP_WP, py = i / HP_WP;
             const int yy = y0 + py - HALO, xx = x0 + px - HALO;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (px < HP_W && yy >= 0 && yy < h && xx >= 0 && xx < w)
-                v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * h + yy) * w + xx) * 64 + c0) + half);
-            s_in[py][half * 4 + 0][px] = v.x; s_in[py][half * 4 + 1][px] = v.y;
-            s_in[py][half * 4 + 2][px] = v.z; s_in[py][half * 4 + 3][px] = v.w;
+                v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * h + yy) * w + xx) * 64 + c0));
+            const int ps = (((px >> 2) ^ ((px >> 5) & 1)) << 2) | (px & 3);      // float4-slot swizzle, see the loads below
+            s_in[py][0][ps] = v.x; s_in[py][1][ps] = v.y; s_in[py][2][ps] = v.z; s_in[py][3][ps] = v.w;
         }
         for (int i = threadIdx.x; i < 49 * HC; i += 128) {
             const int tap = i / HC, c = i % HC;
@@ -53,11 +53,14 @@ __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, c
         for (int ky = 0; ky < 7; ky++) {
 #pragma unroll
             for (int c = 0; c < HC; c++) {
-                float in[12];
-                const float4* src = reinterpret_cast<const float4*>(&s_in[ty + ky][c][tx * 4]);
+                float in[16];
+                // lanes tx and tx+4 of a quarter-warp would hit the same banks (their float4 slots differ by 8):
+                // slots 8..15 are stored with their lowest bit flipped, which makes the 8 accesses conflict-free
+                const float4* src = reinterpret_cast<const float4*>(&s_in[ty + ky][c][0]);
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const float4 a = src[j];
+                for (int j = 0; j < 4; j++) {
+                    const int slot = tx * 2 + j;
+                    const float4 a = src[slot ^ ((slot >> 3) & 1)];
                     in[4 * j] = a.x; in[4 * j + 1] = a.y; in[4 * j + 2] = a.z; in[4 * j + 3] = a.w;
                 }
 #pragma unroll
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, c
                     const float4 wv = *reinterpret_cast<const float4*>(&s_w[ky * 7 + kx][c][0]);
                     const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
-                    for (int p = 0; p < 4; p++) {
+                    for (int p = 0; p < HPX; p++) {
                         const float2 vv = make_float2(in[p + kx], in[p + kx]);
                         acc[p][0] = __ffma2_rn(vv, w01, acc[p][0]);
                         acc[p][1] = __ffma2_rn(vv, w23, acc[p][1]);
@@ -77,8 +80,8 @@ __global__ void __launch_bounds__(128) k_heads7x7(const float* __restrict__ x, c
     const int y = y0 + ty;
     if (y < h) {
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const int xx = x0 + tx * 4 + p;
+        for (int p = 0; p < HPX; p++) {
+            const int xx = x0 + tx * HPX + p;
             if (xx < w)
                 *reinterpret_cast<float4*>(out + (((size_t)b * h + y) * w + xx) * 4) =
                     make_float4(acc[p][0].x, acc[p][0].y, acc[p][1].x, acc[p][1].y);
