@@ -1,0 +1,79 @@
+"""the "kernel to beat" on the same B200 -- the reference's own rasterizer kernels (oracle/_ref,
+compiled unmodified for sm_100a) and the reference generator's ATen ops on the GPU (cuDNN; strict fp32 and TF32) --
+timed next to this library on the BASELINE config-3 batch (16 frames, 256x256).  Writes gpurun_out/stock_compare.json.
+The stock path is the checker/baseline only; nothing here is shipped."""
+import json
+import os
+
+import pytest
+import torch
+
+from impersonator_b200 import synthetic as S
+from impersonator_b200.generator import ImpersonatorGenerator
+from impersonator_b200.nmr import SMPLRenderer
+from oracle import generator_ref as G
+from oracle import nmr_ref, raster
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def test_stock_torch_and_reference_kernels_vs_this_library(cuda):
+    torch.set_grad_enabled(False)
+    B, size = 16, 256
+    n = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    sd = S.fill_state_dict(n.state_dict(), seed=0)
+    n.load_state_dict(sd)
+    n = n.to(cuda).eval()
+    sd_gpu = {k: v.to(cuda) for k, v in sd.items()}
+    inp = S.synthetic_generator_inputs(B, size, seed=21)
+    src, tsf, T = inp["src"][:1].to(cuda), inp["tsf"].to(cuda), inp["T"].to(cuda)
+    out = {"batch": B, "image_size": size}
+
+    # --- generator.inference: stock ATen/cuDNN (the reference modules' ops) -------------------------------
+    enc_o, res_o = G.encode_src(src, sd_gpu)
+    enc_b = [e.expand(B, -1, -1, -1).contiguous() for e in enc_o]          # reference grid_sample needs equal N
+    res_b = [r.expand(B, -1, -1, -1).contiguous() for r in res_o]
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = True
+        ms = timeit(lambda: G.inference(enc_b, res_b, tsf, T, sd_gpu))
+        out["stock_generator_ms_%s" % ("tf32" if tf32 else "fp32")] = ms
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref_img, ref_mask = G.inference(enc_b, res_b, tsf, T, sd_gpu)
+
+    enc, res = n.encode_src(src)
+    out["lwb_generator_ms_fp16x3"] = timeit(lambda: n.inference(enc, res, tsf, T))
+    img, mask = n.inference(enc, res, tsf, T)
+    out["lwb_vs_stock_fp32_max_abs"] = max((img - ref_img).abs().max().item(), (mask - ref_mask).abs().max().item())
+    assert out["lwb_vs_stock_fp32_max_abs"] < 1e-3
+
+    # --- rasterizer: the reference's kernels vs k_face_raster ------------------------------------------------
+    if raster.gpu_ref_available():
+        v, f = S.uv_sphere()
+        cam, verts = S.synthetic_frames(B, seed=1234, base_verts=v)
+        faces = nmr_ref.project_to_faces(cam, verts, f).to(cuda).contiguous()
+        out["reference_raster_kernels_ms"] = timeit(lambda: raster.forward_face_index_map_gpu_ref(faces, size), iters=5, warm=2)
+        tabs = S.synthetic_tables()
+        r = SMPLRenderer(image_size=size, faces=f, map_fn=tabs["map_fn"]).to(cuda)
+        cam_d, verts_d = cam.to(cuda), verts.to(cuda)
+        out["lwb_render_fim_wim_ms"] = timeit(lambda: r.render_fim_wim(cam_d, verts_d))
+    print(json.dumps(out, indent=1))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "stock_compare.json"), "w"), indent=1)
+    assert out["lwb_generator_ms_fp16x3"] < out["stock_generator_ms_fp32"]
