@@ -100,7 +100,7 @@ def cpu_reference_setup(size):
     import torch
     from impersonator_b200 import synthetic as S
     from impersonator_b200.generator import ImpersonatorGenerator
-    from oracle import generator_ref as G, nmr_ref, raster
+    from oracle import generator_ref as G, nmr_ref, raster, smpl_ref
     torch.set_grad_enabled(False)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -109,7 +109,9 @@ def cpu_reference_setup(size):
     src_img = S.synthetic_source(size)
     tmpl = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6).state_dict()
     sd = S.fill_state_dict(tmpl, seed=0)
-    cam, verts = S.synthetic_frames(1, seed=1, base_verts=v)
+    body = smpl_ref.model_tensors(S.synthetic_smpl_model(seed=3))
+    det = smpl_ref.get_details(body, S.synthetic_smpl_params(1, seed=5))
+    cam, verts = det["cam"], det["verts"]
     f2v, fim, _ = nmr_ref.render_fim_wim(cam, verts, f, size)
     p2v = nmr_ref.src_p2verts(f2v)
     src_inputs = torch.cat([src_img, nmr_ref.encode_fim(fim, tabs["map_fn"])], dim=1)
@@ -122,8 +124,9 @@ def cpu_reference_setup(size):
 
     def run(nframes, seed):
         if (nframes, seed) not in frame_sets:                       # synthetic input generation is not timed work
-            frame_sets[(nframes, seed)] = S.synthetic_frames(nframes, seed=seed, base_verts=v)
-        cam, verts = frame_sets[(nframes, seed)]
+            frame_sets[(nframes, seed)] = S.synthetic_smpl_params(nframes, seed=seed)
+        det = smpl_ref.get_details(body, frame_sets[(nframes, seed)])     # SMPL vectors in, like the e2e leg
+        cam, verts = det["cam"], det["verts"]
         c = nmr_ref.correspond(cam, verts, f, tabs["map_fn"], p2v, src_img, size)
         pred, _, _ = G.imitator_forward(bg, feats, c["tsf_inputs"], c["T"], sd)
         return pred
@@ -188,7 +191,7 @@ def run_reference_arm(args):
 
 def workload_config(args, frames_per_step=None):
     return {"workload": "BASELINE configs[2]: batch-%d motion-imitation inference loop (SMPL raster + correspondence + LWB + "
-                        "generator.inference + composite), %dx%d, synthetic UV-sphere body V=6890 F=13776, random-init "
+                        "generator.inference + composite; e2e adds SMPL LBS from 85-float vectors), %dx%d, synthetic SMPL-shaped body V=6890 F=13776, random-init "
                         "ImpersonatorGenerator (97.45 M params)" % (args.batch, args.size, args.size),
             "frames_per_step_per_gpu": frames_per_step if frames_per_step is not None else args.batch,
             "image_size": args.size, "precision": "fp16x3 split on tcgen05 (fp32-equivalent, parity-gated 1e-3)",
@@ -209,7 +212,8 @@ def main():
     from impersonator_b200 import _lib, kernels as K, synthetic as S
     from impersonator_b200 import generator as GEN
     from impersonator_b200.generator import ImpersonatorGenerator
-    from impersonator_b200.imitator import Imitator, SyntheticBodyModel
+    from impersonator_b200.imitator import Imitator
+    from impersonator_b200.hmr import HumanModelRecovery
     from impersonator_b200.nmr import SMPLRenderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,21 +244,14 @@ def main():
     class Opt(object):
         image_size, batch_size, bg_model, repeat_num, cond_nc = size, B, "ORIGINAL", 6, 3
         bg_ks, ft_ks, front_warp, only_vis = 13, 3, False, False
-    body = SyntheticBodyModel(v)
+    body = HumanModelRecovery(smpl_model=S.synthetic_smpl_model(seed=3)).to(dev)       # SMPL LBS kernels (csrc/smpl.cu)
     imitator = Imitator(Opt(), generator=net, hmr=body, render=render, device=dev)
-    src_theta = torch.zeros(85)
-    src_theta[0] = 0.95
+    src_theta = S.synthetic_smpl_params(1, seed=5)[0]
     imitator.personalize("", src_smpl=src_theta.numpy(), src_img=src_img)           # once per source (untimed)
 
     # per-step target frames: 4 rotating sets per rank, resident in HBM for `value`
     def thetas(seed):
-        g = torch.Generator().manual_seed(seed)
-        th = torch.zeros(B, 85)
-        th[:, 0] = 0.8 + 0.3 * torch.rand(B, generator=g)
-        th[:, 1:3] = (torch.rand(B, 2, generator=g) * 2 - 1) * 0.1
-        th[:, 3] = (torch.rand(B, generator=g) * 2 - 1) * 3.14159
-        th[:, 4] = (torch.rand(B, generator=g) * 2 - 1) * 0.3
-        return th
+        return S.synthetic_smpl_params(B, seed=seed)
     host_sets = [thetas(1000 + 17 * rank + i) for i in range(4)]
     imitator.first_cam = host_sets[0][0:1, 0:3].to(dev)
     dev_sets = []
@@ -317,6 +314,11 @@ def main():
     prof_flag, args.profile_range = args.profile_range, False
     ms_e2e, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
     e2e_fps = world * B * args.steps / (ms_e2e * 1e-3)
+
+    def step_e2e_u8(i):
+        outs = imitator.inference_by_smpls(list(pinned[i % len(pinned)]), cam_strategy="smooth", as_uint8=True)
+        assert len(outs) == B and outs[0].dtype.itemsize == 1
+    ms_u8, _ = timed(step_e2e_u8, args.steps, 3)
     args.profile_range = prof_flag
 
     line = {"metric": "frames/sec @256x256 (per-frame inference hot path)", "value": fps, "unit": "frames/s",
@@ -325,7 +327,11 @@ def main():
             "dtype": "f16 (3-term hi/lo split, f32 accumulate)", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "api": "Imitator.inference_by_smpls(host SMPL vectors) -> host float32 frames"},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "Imitator.inference_by_smpls(host SMPL vectors) -> SMPL LBS -> ... -> host float32 HxWx3 frames",
+                    "uint8_frames": {"value": world * B * args.steps / (ms_u8 * 1e-3), "unit": "frames/s",
+                                     "d2h_bytes_per_step": B * 3 * size * size,
+                                     "note": "same call with as_uint8=True: the BGR uint8 images the reference writes to disk"}},
             "gpu_launches": launches, "clocks": clocks}
 
     # ---- roofline of the conv engine + per-kernel-class breakdown (instrumented passes, rank 0) ---

@@ -273,9 +273,15 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
 // ---------------------------------------------------------------------------------------------
 // heads: color = tanh(raw[0:3]), mask = sigmoid(raw[3]), pred = mask*bg + (1-mask)*color
 // ---------------------------------------------------------------------------------------------
+// numpy's ((img + 1) / 2.0 * 255).astype(uint8) of cv_utils.save_cv2_img (utils/cv_utils.py:31-33): fp32, truncation
+__device__ __forceinline__ uint8_t to_u8(float x) {
+    return (uint8_t)__float2int_rz(__fmul_rn(__fmul_rn(__fadd_rn(x, 1.f), 0.5f), 255.f));
+}
+
 __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ raw, int n, int hw, int c_stride,
                                                const float* __restrict__ bg, int bg_batch,
-                                               float* __restrict__ color, float* __restrict__ mask, float* __restrict__ pred)
+                                               float* __restrict__ color, float* __restrict__ mask, float* __restrict__ pred,
+                                               float* __restrict__ pred_hwc, uint8_t* __restrict__ pred_u8_bgr)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)n * hw) return;
@@ -287,10 +293,28 @@ __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ raw, in
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         if (color) color[((size_t)b * 3 + k) * hw + p] = col[k];
-        if (pred && bg) {
+        if (bg) {
             const float bgv = __ldg(bg + ((size_t)(bg_batch == 1 ? 0 : b) * 3 + k) * hw + p);
-            pred[((size_t)b * 3 + k) * hw + p] = m * bgv + (1.f - m) * col[k];
+            const float pv = m * bgv + (1.f - m) * col[k];
+            if (pred) pred[((size_t)b * 3 + k) * hw + p] = pv;
+            if (pred_hwc) pred_hwc[(size_t)i * 3 + k] = pv;                      // preds[0].permute(1, 2, 0)  (imitator.py:178)
+            if (pred_u8_bgr) pred_u8_bgr[(size_t)i * 3 + (2 - k)] = to_u8(pv);   // RGB2BGR + normalize (cv_utils.py:24-33)
         }
+    }
+}
+
+// Output path for frames that did not come straight out of k_heads (e.g. after warp_front): NCHW fp32 -> HWC fp32 / BGR u8
+__global__ void __launch_bounds__(256) k_frames_out(const float* __restrict__ x, int n, int hw,
+                                                    float* __restrict__ hwc, uint8_t* __restrict__ u8_bgr)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n * hw) return;
+    const int b = (int)(i / hw), p = (int)(i % hw);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float v = __ldg(x + ((size_t)b * 3 + k) * hw + p);
+        if (hwc) hwc[(size_t)i * 3 + k] = v;
+        if (u8_bgr) u8_bgr[(size_t)i * 3 + (2 - k)] = to_u8(v);
     }
 }
 
@@ -416,13 +440,24 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
 
 extern "C" int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride,
                                    const float* bg, int bg_batch,
-                                   float* color, float* mask, float* pred, lwb_stream_t stream)
+                                   float* color, float* mask, float* pred,
+                                   float* pred_hwc, uint8_t* pred_u8_bgr, lwb_stream_t stream)
 {
     LWB_CHECK_ARG(raw, "null pointer");
+    LWB_CHECK_ARG(bg || (!pred && !pred_hwc && !pred_u8_bgr), "the composite outputs need bg");
     LWB_CHECK_ARG(n > 0 && h > 0 && w > 0 && c_stride >= 4 && (c_stride % 4) == 0, "bad sizes");
     LWB_CHECK_ARG(!bg || bg_batch == 1 || bg_batch == n, "bg_batch must be 1 or n");
     k_heads<<<lwb::ceil_div((long)n * h * w, 256), 256, 0, (cudaStream_t)stream>>>(
-        raw, n, h * w, c_stride, bg, bg_batch, color, mask, pred);
+        raw, n, h * w, c_stride, bg, bg_batch, color, mask, pred, pred_hwc, pred_u8_bgr);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+extern "C" int lwb_frames_out(const float* frames, int n, int h, int w, float* hwc, uint8_t* u8_bgr, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(frames && (hwc || u8_bgr), "null pointer");
+    LWB_CHECK_ARG(n > 0 && h > 0 && w > 0, "bad sizes");
+    k_frames_out<<<lwb::ceil_div((long)n * h * w, 256), 256, 0, (cudaStream_t)stream>>>(frames, n, h * w, hwc, u8_bgr);
     LWB_LAUNCH_OK();
     return LWB_OK;
 }

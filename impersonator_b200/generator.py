@@ -298,12 +298,12 @@ class _UnetStream(_StreamBase):
             self._conv_norm(ld, self.d_up[i], True)
             self._conv_norm(ls, self.d_out[i], True)
 
-    def heads(self, bg=None, want_color=True, want_mask=True):
+    def heads(self, bg=None, want_color=True, want_mask=True, **out):
         if self.head_layer is not None:
             self.head_layer.plan.run()
         else:
             K.conv7x7_heads_nhwc(self.d_out[-1].f32, self.w4, out=self.head_raw)
-        return K.heads_composite(self.head_raw, bg, want_color=want_color, want_mask=want_mask)
+        return K.heads_composite(self.head_raw, bg, want_color=want_color, want_mask=want_mask, **out)
 
     def encoder_outs_nchw(self):
         outs = []
@@ -593,9 +593,11 @@ class ImpersonatorGenerator(NetworkBase):
         return tsf_img, tsf_mask
 
     @torch.no_grad()
-    def inference(self, src_encoder_outs, src_resnet_outs, tsf_inputs, T, bg=None):
+    def inference(self, src_encoder_outs, src_resnet_outs, tsf_inputs, T, bg=None, pred_hwc=None, pred_u8=None):
         """networks/generator.py:277-301.  With ``bg`` also returns the composite of
-        models/imitator.py:331 as a third value (fused into the head kernel)."""
+        models/imitator.py:331 as a third value (fused into the head kernel); ``pred_hwc`` / ``pred_u8``
+        (caller-allocated [B,H,W,3] float32 / uint8-BGR) receive the same frames in the layouts of the output
+        path (models/imitator.py:178-180, utils/cv_utils.py:23-36) from that launch."""
         ac = _align_corners()
         tsf = self.tsf_model._stream(tsf_inputs, False, 'inference')
         tsf.load_input(tsf_inputs.float())
@@ -603,7 +605,12 @@ class ImpersonatorGenerator(NetworkBase):
         tsf.encode(warp_srcs=[None] + [_nhwc_of(a) for a in src_encoder_outs[1:]], T=T, ac=ac)
         tsf.resnets(warp_srcs=[_nhwc_of(a) for a in src_resnet_outs], T=T, ac=ac)
         tsf.decode()
-        color, mask, pred = tsf.heads(bg)
+        if pred_hwc is not None or pred_u8 is not None:
+            if bg is None:
+                raise LwbError("pred_hwc / pred_u8 need bg (they hold the composite)")
+            color, mask, pred = tsf.heads(bg, pred_hwc=pred_hwc, pred_u8=pred_u8)
+        else:
+            color, mask, pred = tsf.heads(bg)
         if bg is not None:
             return color, mask, pred
         return color, mask

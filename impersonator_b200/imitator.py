@@ -214,11 +214,28 @@ class Imitator(object):
 
     # ---- generator + composite (models/imitator.py:326-342) -----------------------------------
     @torch.no_grad()
-    def forward(self, tsf_inputs, T):
+    def forward(self, tsf_inputs, T, host_layout=None):
+        """-> preds [B,3,H,W].  ``host_layout`` = dict(hwc=bool, u8=bool) additionally fills
+        ``self._out_hwc`` / ``self._out_u8`` ([B,H,W,3] float32 / uint8 BGR, the output path of
+        models/imitator.py:178-187) -- from the head kernel itself unless warp_front rewrites the frames."""
         enc, res = self.src_info['feats']
-        color, mask, pred = self.generator.inference(enc, res, tsf_inputs, T, bg=self.src_info['bg'])
-        if getattr(self._opt, 'front_warp', False):
-            pred = self.warp_front(pred, mask)
+        front = getattr(self._opt, 'front_warp', False)
+        hwc = u8 = None
+        if host_layout:
+            B, _, H, W = tsf_inputs.shape
+            hwc = torch.empty((B, H, W, 3), dtype=torch.float32, device=self.device) if host_layout.get('hwc') else None
+            u8 = torch.empty((B, H, W, 3), dtype=torch.uint8, device=self.device) if host_layout.get('u8') else None
+        if front or not host_layout:
+            color, mask, pred = self.generator.inference(enc, res, tsf_inputs, T, bg=self.src_info['bg'])
+            if front:
+                pred = self.warp_front(pred, mask)
+            if host_layout:
+                from . import kernels as K
+                hwc, u8 = K.frames_out(pred.contiguous(), want_hwc=hwc is not None, want_u8=u8 is not None)
+        else:
+            color, mask, pred = self.generator.inference(enc, res, tsf_inputs, T, bg=self.src_info['bg'],
+                                                         pred_hwc=hwc, pred_u8=u8)
+        self._out_hwc, self._out_u8 = hwc, u8
         return pred
 
     def warp_front(self, preds, mask):
@@ -231,7 +248,11 @@ class Imitator(object):
         return [(i, min(n, i + bs)) for i in range(0, n, bs)]
 
     @torch.no_grad()
-    def inference(self, tgt_paths, tgt_smpls=None, cam_strategy='smooth', output_dir='', visualizer=None, verbose=True):
+    def inference(self, tgt_paths, tgt_smpls=None, cam_strategy='smooth', output_dir='', visualizer=None, verbose=True,
+                  as_uint8=False):
+        """models/imitator.py:157-189.  Returns per-frame float32 HxWx3 arrays in [-1,1] like the reference; with
+        ``as_uint8=True`` (extra) returns the BGR uint8 images the reference writes to disk instead (4x less D2H).
+        With ``output_dir`` the uint8 images come from the GPU and go straight to cv2.imwrite."""
         length = len(tgt_paths)
         outputs = []
         if tgt_smpls is None:
@@ -245,26 +266,31 @@ class Imitator(object):
         for (a, b) in self._chunks(length):
             smpls = torch.as_tensor(np.stack([np.asarray(s, dtype=np.float32) for s in tgt_smpls[a:b]]))
             tsf_inputs = self.transfer_params_by_smpl(smpls, cam_strategy, t=a)
-            preds = self.forward(tsf_inputs, self.tsf_info['T'])
+            want_u8 = bool(as_uint8 or output_dir)
+            preds = self.forward(tsf_inputs, self.tsf_info['T'], host_layout=dict(hwc=not as_uint8, u8=want_u8))
             if visualizer is not None:
                 visualizer.vis_named_img('pred_' + cam_strategy, preds)
-            host = self._to_host(preds.permute(0, 2, 3, 1).contiguous())       # one D2H + sync per chunk
+            host_u8 = self._to_host(self._out_u8, sync=as_uint8) if want_u8 else None
+            host = host_u8 if as_uint8 else self._to_host(self._out_hwc)        # one sync per chunk
             for j in range(b - a):
                 outputs.append(host[j])
-                self._maybe_save(host[j], tgt_paths[a + j], output_dir, a + j)
+                if output_dir:
+                    self._maybe_save(host_u8[j], tgt_paths[a + j], output_dir, a + j, is_bgr_u8=True)
         self._last_frame_info()
         return outputs
 
     @torch.no_grad()
-    def inference_by_smpls(self, tgt_smpls, cam_strategy='smooth', output_dir='', visualizer=None):
-        return self.inference([''] * len(tgt_smpls), tgt_smpls, cam_strategy, output_dir, visualizer, verbose=False)
+    def inference_by_smpls(self, tgt_smpls, cam_strategy='smooth', output_dir='', visualizer=None, as_uint8=False):
+        return self.inference([''] * len(tgt_smpls), tgt_smpls, cam_strategy, output_dir, visualizer, verbose=False,
+                              as_uint8=as_uint8)
 
     @staticmethod
-    def _to_host(t):
-        """Device -> pinned host (torch's caching host allocator), one async copy + one sync."""
+    def _to_host(t, sync=True):
+        """Device -> pinned host (torch's caching host allocator), one async copy (+ one sync)."""
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if sync:
+            torch.cuda.current_stream().synchronize()
         return h.numpy()
 
     def _last_frame_info(self):
@@ -274,11 +300,16 @@ class Imitator(object):
             if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] > 1:
                 info[k] = v[-1:]
 
-    def _maybe_save(self, pred, tgt_path, output_dir, t):
+    def _maybe_save(self, pred, tgt_path, output_dir, t, is_bgr_u8=False):
         if not output_dir:
             return
         name = os.path.split(tgt_path)[-1] if tgt_path else 'pred_%.8d.jpg' % t
-        _save_image(pred, os.path.join(output_dir, 'pred_' + name if tgt_path else name), normalize=True)
+        path = os.path.join(output_dir, 'pred_' + name if tgt_path else name)
+        if is_bgr_u8:
+            import cv2
+            cv2.imwrite(path, pred)                      # already what save_cv2_img(normalize=True) would write
+        else:
+            _save_image(pred, path, normalize=True)
 
     def post_personalize(self, *a, **k):
         raise LwbError("post_personalize (fine-tuning) needs the backward pass: outside the inference hot path")

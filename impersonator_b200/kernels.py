@@ -309,21 +309,42 @@ def conv7x7_heads_nhwc(x, w4, out=None):
     return out
 
 
-def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, mask=None, pred=None):
-    _chk_cuda(raw, bg, color, mask, pred)
+def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, mask=None, pred=None,
+                    want_pred=True, pred_hwc=None, pred_u8=None):
+    """-> color, mask, pred (NCHW).  ``pred_hwc`` f32 [n,h,w,3] / ``pred_u8`` uint8 BGR [n,h,w,3]: caller-allocated
+    output-path buffers filled by the same launch."""
+    _chk_cuda(raw, bg, color, mask, pred, pred_hwc, pred_u8)
     n, h, w, cs = raw.shape
     dev = raw.device
     if color is None and want_color:
         color = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
     if mask is None and want_mask:
         mask = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
-    if pred is None and bg is not None:
+    if pred is None and bg is not None and want_pred:
         pred = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+    for t, dt in ((pred_hwc, torch.float32), (pred_u8, torch.uint8)):
+        if t is not None and (t.dtype != dt or tuple(t.shape) != (n, h, w, 3)):
+            raise LwbError("output-path buffers must be [n,h,w,3] float32 / uint8")
     _count(1)
     with _Prof("heads", 0.0):
         check(lib().lwb_heads_composite(ptr(raw), n, h, w, cs, ptr(bg), bg.shape[0] if bg is not None else 0,
-                                        ptr(color), ptr(mask), ptr(pred), stream()), "lwb_heads_composite")
+                                        ptr(color), ptr(mask), ptr(pred), ptr(pred_hwc), ptr(pred_u8), stream()),
+              "lwb_heads_composite")
     return color, mask, pred
+
+
+def frames_out(frames, want_hwc=True, want_u8=False):
+    """[n,3,h,w] fp32 -> (hwc f32 [n,h,w,3] | None, u8 BGR [n,h,w,3] | None): models/imitator.py:178-180 +
+    utils/cv_utils.py:23-36."""
+    _chk_cuda(frames)
+    n, c, h, w = frames.shape
+    if c != 3 or frames.dtype != torch.float32:
+        raise LwbError("frames must be float32 [n,3,h,w]")
+    hwc = torch.empty((n, h, w, 3), dtype=torch.float32, device=frames.device) if want_hwc else None
+    u8 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=frames.device) if want_u8 else None
+    _count(1)
+    check(lib().lwb_frames_out(ptr(frames), n, h, w, ptr(hwc), ptr(u8), stream()), "lwb_frames_out")
+    return hwc, u8
 
 
 def conv2d_direct_nchw(x, w, bias=None, stride=1, pad=0, dil=1):
@@ -346,3 +367,39 @@ def gated_bn_nchw(ab, act, scale=None, shift=None):
     check(lib().lwb_gated_bn_nchw(ptr(ab), n, c2 // 2, h, w, act, ptr(scale), ptr(shift), ptr(out), stream()),
           "lwb_gated_bn_nchw")
     return out
+
+
+def smpl_forward(beta, theta, model, rotate_base=False, cam=None, want_joints=True):
+    """SMPL.forward (networks/batch_smpl.py:285-375) through lwb_smpl_forward.  ``model``: dict of device
+    tensors (see impersonator_b200.smpl.SMPL._device_model).  -> verts [B,V,3], joints [B,NJ,3] | None,
+    Rs [B,24,3,3], J_transformed [B,24,3], j2d [B,NJ,2] | None."""
+    _chk_cuda(beta, theta, cam)
+    if beta.dtype != torch.float32 or theta.dtype != torch.float32:
+        raise LwbError("beta/theta must be float32")
+    B = beta.shape[0]
+    if theta.shape != (B, 72):
+        raise LwbError("theta must be [B,72]")
+    dev = beta.device
+    V = model["v_template"].shape[0]
+    nb = model["shapedirs"].shape[0]
+    if beta.shape[1] != nb:
+        raise LwbError("beta must be [B,%d]" % nb)
+    nj = model["joint_regressor_t"].shape[0]
+    verts = torch.empty(B, V, 3, dtype=torch.float32, device=dev)
+    Rs = torch.empty(B, 24, 3, 3, dtype=torch.float32, device=dev)
+    Jt = torch.empty(B, 24, 3, dtype=torch.float32, device=dev)
+    joints = torch.empty(B, nj, 3, dtype=torch.float32, device=dev) if want_joints else None
+    j2d = torch.empty(B, nj, 2, dtype=torch.float32, device=dev) if (want_joints and cam is not None) else None
+    key = (dev.index, "smpl")
+    n = lib().lwb_smpl_workspace_bytes(B)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = _ws_cache[key] = torch.empty(n, dtype=torch.uint8, device=dev)
+    check(lib().lwb_smpl_forward(
+        ptr(beta), ptr(theta), B, nb, V, ptr(model["v_template"]), ptr(model["shapedirs"]), ptr(model["posedirs"]),
+        ptr(model["j_template"]), ptr(model["j_shapedirs"]), ptr(model["parents"]), ptr(model["weights"]),
+        ptr(model["joint_regressor_t"]), nj, 1 if rotate_base else 0,
+        ptr(verts), ptr(joints), ptr(Rs), ptr(Jt), ptr(cam if j2d is not None else None), ptr(j2d), ptr(ws), stream()),
+        "lwb_smpl_forward")
+    _count(3 if want_joints else 2)
+    return verts, joints, Rs, Jt, j2d

@@ -1,0 +1,79 @@
+"""SMPL body model on the B200 kernels -- the host-side mirror of ``networks/batch_smpl.py`` (class ``SMPL``,
+:235-375) for the per-frame path ``HumanModelRecovery.get_details`` (networks/hmr.py:302-330) drives.
+
+Same constructor (``pkl_path``, ``rotate``), same registered buffers (``v_template, shapedirs, J_regressor,
+posedirs, weights, joint_regressor``: checkpoints / model files load unchanged), same ``forward(beta, theta,
+get_skin)`` results.  The math runs in ``csrc/smpl.cu`` (three launches per batch); there is no torch fallback.
+``model=`` accepts the unpickled dict directly (tests use impersonator_b200.synthetic.synthetic_smpl_model
+because smpl_model.pkl is an external download).
+"""
+import pickle
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from ._lib import LwbError
+
+
+def batch_orth_proj_idrot(X, camera):
+    """networks/batch_smpl.py:221-233 (tiny; the per-frame path gets j2d from the joints kernel instead)."""
+    return camera[:, None, 0:1] * (X[:, :, :2] + camera[:, None, 1:])
+
+
+class SMPL(nn.Module):
+    def __init__(self, pkl_path=None, rotate=False, model=None):
+        super(SMPL, self).__init__()
+        self.rotate = rotate
+        if model is None:
+            if pkl_path is None:
+                raise LwbError("SMPL needs pkl_path= (smpl_model.pkl) or model= (its unpickled dict)")
+            with open(pkl_path, 'rb') as f:
+                model = pickle.load(f, encoding='latin1')          # utils/util.py:235-239
+        dd = model
+        self.faces = torch.from_numpy(np.asarray(dd['f']).astype(np.int32)).type(dtype=torch.int32)
+        self.register_buffer('v_template', torch.FloatTensor(np.asarray(dd['v_template'])))
+        self.size = [self.v_template.shape[0], 3]
+        self.num_betas = dd['shapedirs'].shape[-1]
+        self.register_buffer('shapedirs', torch.FloatTensor(np.reshape(dd['shapedirs'], [-1, self.num_betas]).T.copy()))
+        self.register_buffer('J_regressor', torch.FloatTensor(np.asarray(dd['J_regressor'].T.todense())))
+        num_pose_basis = dd['posedirs'].shape[-1]
+        self.register_buffer('posedirs', torch.FloatTensor(np.reshape(dd['posedirs'], [-1, num_pose_basis]).T.copy()))
+        self.parents = np.array(dd['kintree_table'][0].astype(np.int32))
+        self.register_buffer('weights', torch.FloatTensor(np.asarray(dd['weights'])))
+        self.register_buffer('joint_regressor', torch.FloatTensor(np.asarray(dd['cocoplus_regressor'].T.todense())))
+        if num_pose_basis != 207 or self.parents.shape[0] != 24 or self.weights.shape[1] != 24:
+            raise LwbError("the kernels are specialised for SMPL's 24 joints / 207 pose basis")
+        self._dm = None
+        self.J_transformed = None
+
+    def _device_model(self):
+        """Model tensors in the kernel's layout, built once per device.  The joint regression of
+        batch_smpl.py:318-321 is linear in beta, so J = J0 + JS beta with J0 = J_regressor^T v_template and
+        JS = J_regressor^T shapedirs folded here (float64, once)."""
+        dev = self.v_template.device
+        if self._dm is not None and self._dm["v_template"].device == dev and self._dm["_src"] is self.v_template:
+            return self._dm
+        V = self.size[0]
+        Jr = self.J_regressor.double().t()                                       # [24, V]
+        j_template = (Jr @ self.v_template.double()).float().contiguous()        # [24, 3]
+        sd = self.shapedirs.double().view(self.num_betas, V, 3)                  # [NB, V, 3]
+        j_shapedirs = torch.einsum('jv,kvd->jdk', Jr, sd).reshape(72, self.num_betas).float().contiguous()
+        self._dm = dict(v_template=self.v_template.contiguous(), shapedirs=self.shapedirs.contiguous(),
+                        posedirs=self.posedirs.contiguous(), weights=self.weights.contiguous(),
+                        j_template=j_template, j_shapedirs=j_shapedirs,
+                        parents=torch.as_tensor(self.parents.astype(np.int32), device=dev),
+                        joint_regressor_t=self.joint_regressor.t().contiguous(), _src=self.v_template)
+        return self._dm
+
+    def forward(self, beta, theta, get_skin=False, cam=None):
+        """beta [N,10], theta [N,72] -> joints [N,19,3]  (get_skin: verts [N,6890,3], joints, Rs [N,24,3,3]).
+        ``cam`` (extra, optional): also project the joints (``self.j2d``)."""
+        verts, joints, Rs, Jt, j2d = K.smpl_forward(beta.contiguous(), theta.contiguous(), self._device_model(),
+                                                    rotate_base=self.rotate, cam=cam)
+        self.J_transformed = Jt
+        self.j2d = j2d
+        if get_skin:
+            return verts, joints, Rs
+        return joints

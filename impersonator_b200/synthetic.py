@@ -165,3 +165,61 @@ def synthetic_generator_inputs(batch, image_size=256, seed=11):
     r = lambda *s: torch.rand(*s, generator=g) * 2 - 1
     return dict(bg=r(1, 4, image_size, image_size), src=r(1, 6, image_size, image_size),
                 tsf=r(batch, 6, image_size, image_size), T=synthetic_flow(batch, image_size, seed + 1))
+
+
+# SMPL kinematic tree (kintree_table[0] of the public SMPL model; entry 0 is the root, stored as uint32 -1)
+SMPL_PARENTS = (-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21)
+
+
+def synthetic_smpl_model(seed=3, num_betas=10, num_joints=19):
+    """A stand-in for ``smpl_model.pkl`` (external, not redistributable) with the SAME keys, shapes and
+    dtypes that ``SMPL.__init__`` reads (networks/batch_smpl.py:236-283): the UV-sphere body as template,
+    random blend shapes, banded joint regressors and 4-joint skinning weights.  numpy / scipy.sparse only."""
+    import scipy.sparse as sp
+    rs = np.random.RandomState(seed)
+    v, f = uv_sphere()
+    v = v.numpy().astype(np.float64)
+    V = v.shape[0]
+    order = np.argsort(v[:, 1], kind="stable")                 # bottom to top
+    band = np.empty(V, dtype=np.int64)
+    band[order] = (np.arange(V) * 24) // V                        # 24 height bands <-> 24 joints
+
+    def banded(rows, per_row):
+        m = np.zeros((rows, V), dtype=np.float64)
+        for j in range(rows):
+            cand = np.nonzero(band == (j * 24) // rows)[0]
+            idx = rs.choice(cand, size=per_row, replace=False)
+            w = rs.rand(per_row) + 0.1
+            m[j, idx] = w / w.sum()
+        return sp.csc_matrix(m)
+
+    weights = np.zeros((V, 24), dtype=np.float64)
+    for k, off in enumerate((0, -1, 1, 2)):
+        j = np.clip(band + off, 0, 23)
+        weights[np.arange(V), j] += (0.55, 0.2, 0.15, 0.1)[k] * (0.5 + rs.rand(V))
+    weights /= weights.sum(axis=1, keepdims=True)
+    kintree = np.zeros((2, 24), dtype=np.uint32)
+    kintree[0] = np.array(SMPL_PARENTS, dtype=np.int64).astype(np.uint32)
+    kintree[1] = np.arange(24)
+    return {
+        "f": f.numpy().astype(np.uint32),
+        "v_template": v,
+        "shapedirs": rs.randn(V, 3, num_betas) * 0.01,
+        "posedirs": rs.randn(V, 3, 207) * 0.004,
+        "J_regressor": banded(24, 40),
+        "kintree_table": kintree,
+        "weights": weights,
+        "cocoplus_regressor": banded(num_joints, 24),
+    }
+
+
+def synthetic_smpl_params(batch, seed=17):
+    """-> theta f32[B,85] = [cam(3) | pose(72) | shape(10)] (the layout of networks/hmr.py:314-316)."""
+    g = torch.Generator().manual_seed(seed)
+    cam = torch.stack([0.8 + 0.3 * torch.rand(batch, generator=g), torch.rand(batch, generator=g) * 0.2 - 0.1,
+                       torch.rand(batch, generator=g) * 0.2 - 0.1], dim=1)
+    pose = torch.randn(batch, 72, generator=g) * 0.25
+    pose[:, 0:3] = torch.stack([torch.randn(batch, generator=g) * 0.2, (torch.rand(batch, generator=g) * 2 - 1) * math.pi,
+                                torch.randn(batch, generator=g) * 0.1], dim=1)
+    shape = torch.randn(batch, 10, generator=g)
+    return torch.cat([cam, pose, shape], dim=1).float()

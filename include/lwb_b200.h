@@ -178,10 +178,18 @@ int lwb_conv7x7_heads_nhwc(const float* x, const float* w4, int n, int h, int w,
 /* Output heads + composite:  color = tanh(raw[...,0:3]), mask = sigmoid(raw[...,3]),
  * pred = mask*bg + (1-mask)*color   (networks/generator.py:183-184, models/imitator.py:330-331).
  * raw [n,h,w,c_stride] fp32 NHWC (channels 0..3 used); bg [bg_batch,3,h,w] NCHW (nullable -> no pred).
- * color [n,3,h,w], mask [n,1,h,w], pred [n,3,h,w] NCHW, each nullable. */
+ * color [n,3,h,w], mask [n,1,h,w], pred [n,3,h,w] NCHW, each nullable.
+ * Output path, each nullable: pred_hwc [n,h,w,3] fp32 = preds.permute(1,2,0) of
+ * models/imitator.py:178-180; pred_u8_bgr [n,h,w,3] uint8 = the image cv_utils.save_cv2_img(normalize=True) hands to
+ * cv2.imwrite (utils/cv_utils.py:23-36: RGB->BGR, ((x+1)/2*255) in fp32, truncated). */
 int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride,
                         const float* bg, int bg_batch,
-                        float* color, float* mask, float* pred, lwb_stream_t stream);
+                        float* color, float* mask, float* pred,
+                        float* pred_hwc, uint8_t* pred_u8_bgr, lwb_stream_t stream);
+
+/* The same output-path conversion for frames [n,3,h,w] NCHW fp32 that did not come straight out of the heads
+ * (e.g. after Imitator.warp_front, models/imitator.py:338-342). */
+int lwb_frames_out(const float* frames, int n, int h, int w, float* hwc, uint8_t* u8_bgr, lwb_stream_t stream);
 
 /* Direct (CUDA-core) convolution, NCHW fp32, arbitrary kernel / stride / dilation, optional bias:
  * the once-per-source inpaintor layers (networks/inpaintor.py:12-47) and odd shapes. */
@@ -194,6 +202,25 @@ int lwb_conv2d_direct_nchw(const float* x, const float* w, const float* bias,
  * (eval-mode BatchNorm2d folded; scale/shift nullable).  act: 0 none, 1 ReLU, 2 LeakyReLU(0.2). */
 int lwb_gated_bn_nchw(const float* ab, int n, int c, int h, int w, int act,
                       const float* scale, const float* shift, float* out, lwb_stream_t stream);
+
+/* ---- SMPL body model: pose -> vertices -------------------------------------------------
+ * Replaces SMPL.forward (networks/batch_smpl.py:285-375; batch_rodrigues :64-101, batch_global_rigid_transformation
+ * :129-218) as called by HumanModelRecovery.get_details (networks/hmr.py:302-330).
+ * beta [B,num_betas], theta [B,72] axis-angle (global rotation first).  Model tensors (device, fp32):
+ *   v_template [V,3]; shapedirs [num_betas][V*3]; posedirs [207][V*3]   (the registered buffers of batch_smpl.py:254-273)
+ *   j_template [24,3] = J_regressor^T v_template and j_shapedirs [24*3][num_betas] = J_regressor^T shapedirs
+ *       (the joint regression of :318-321 is linear in beta, so it is folded into the model once at load time);
+ *   parents int32[24] (kintree_table[0]); weights [V,24]; joint_regressor_t [num_joints][V] (cocoplus, transposed).
+ * Outputs: verts [B,V,3]; joints [B,num_joints,3] (nullable); Rs [B,24,3,3] (nullable); J_transformed [B,24,3]
+ * (nullable); j2d [B,num_joints,2] (nullable) = cam_s * (joints_xy + cam_t) with cam [B,3] (batch_orth_proj_idrot,
+ * batch_smpl.py:221-233).  workspace: lwb_smpl_workspace_bytes(B) bytes. */
+size_t lwb_smpl_workspace_bytes(int batch);
+int lwb_smpl_forward(const float* beta, const float* theta, int batch, int num_betas, int num_verts,
+                     const float* v_template, const float* shapedirs, const float* posedirs,
+                     const float* j_template, const float* j_shapedirs, const int* parents,
+                     const float* weights, const float* joint_regressor_t, int num_joints, int rotate_base,
+                     float* verts, float* joints, float* Rs, float* J_transformed,
+                     const float* cam, float* j2d, void* workspace, lwb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -56,3 +56,17 @@ def test_python_front_end_refuses_cpu_tensors():
     from impersonator_b200 import kernels as K
     with pytest.raises(_lib.LwbError):
         K.warp_nchw(torch.zeros(1, 3, 8, 8), torch.zeros(1, 8, 8, 2))
+
+
+def test_smpl_argument_checks(L):
+    dummy = ctypes.c_void_p(1024)
+    args = lambda **o: [o.get("beta", dummy), dummy, o.get("batch", 2), o.get("nb", 10), 6890, dummy, dummy, dummy, dummy, dummy,
+                        dummy, dummy, o.get("reg", dummy), 19, 0, o.get("verts", dummy), o.get("joints", dummy), None, None,
+                        o.get("cam", None), o.get("j2d", None), dummy, None]
+    assert L.lwb_smpl_forward(*args(beta=None)) == -1 and b"null" in L.lwb_last_error()
+    assert L.lwb_smpl_forward(*args(batch=0)) == -1 and b"positive" in L.lwb_last_error()
+    assert L.lwb_smpl_forward(*args(nb=17)) == -1 and b"num_betas" in L.lwb_last_error()
+    assert L.lwb_smpl_forward(*args(reg=None)) == -1 and b"regressor" in L.lwb_last_error()
+    assert L.lwb_smpl_forward(*args(j2d=dummy)) == -1 and b"j2d" in L.lwb_last_error()
+    assert L.lwb_smpl_workspace_bytes(0) == 0
+    assert L.lwb_smpl_workspace_bytes(3) == 3 * (207 + 24 * 12) * 4

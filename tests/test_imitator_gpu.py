@@ -78,3 +78,118 @@ def test_imitator_inference_matches_oracle(cuda):
     print("Imitator.inference_by_smpls vs oracle loop: max-abs %.3e over 5 frames" % worst)
     assert worst < 1e-3
     assert im.tsf_info["T"].shape[0] == 1                                    # tsf_info describes the last frame
+
+
+def test_imitator_from_smpl_vectors_through_lbs_kernels(cuda):
+    """85-float SMPL vectors in, frames out, with the SMPL LBS kernels as the body model (HumanModelRecovery.get_details,
+    networks/hmr.py:302-330).  LBS parity itself is tests/test_smpl_gpu.py; here the oracle loop consumes the vertices the
+    kernels produced, so that 1e-7 vertex differences cannot flip silhouette pixels of the bit-exact rasterizer."""
+    from impersonator_b200.hmr import HumanModelRecovery
+    from oracle import smpl_ref
+    torch.set_grad_enabled(False)
+    size = 256
+    v, f = S.uv_sphere()
+    tabs = S.synthetic_tables()
+    net = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    sd = S.fill_state_dict(net.state_dict(), seed=0)
+    net.load_state_dict(sd)
+    render = SMPLRenderer(image_size=size, faces=f.numpy(), map_fn=tabs["map_fn"])
+    dd = S.synthetic_smpl_model(seed=3)
+    body = HumanModelRecovery(smpl_model=dd).to(cuda)
+    opt = Opt()
+    opt.batch_size = 3
+    im = Imitator(opt, generator=net, hmr=body, render=render, device=cuda)
+    src_img = S.synthetic_source(size)
+    src_theta = S.synthetic_smpl_params(1, seed=5)
+    im.personalize("", src_smpl=src_theta[0].numpy(), src_img=src_img)
+    tgt = S.synthetic_smpl_params(4, seed=77)
+    outs = im.inference_by_smpls(list(tgt.numpy()), cam_strategy="smooth")          # chunks of 3, 1
+    assert len(outs) == 4
+    assert im.tsf_info["j2d"].shape == (1, 19, 2) and im.tsf_info["verts"].shape == (1, 6890, 3)
+
+    m = smpl_ref.model_tensors(dd)
+    sinfo = smpl_ref.get_details(m, src_theta)
+    assert (im.src_info["verts"].cpu() - sinfo["verts"]).abs().max() < 1e-5
+    s_verts = im.src_info["verts"].cpu()
+    f2v, sfim, _ = nmr_ref.render_fim_wim(sinfo["cam"], s_verts, f, size)
+    cond = nmr_ref.encode_fim(sfim, tabs["map_fn"])
+    p2v = nmr_ref.src_p2verts(f2v)
+    bg_mask = ref_morph(cond[:, -1:], 13, 'erode')
+    bg = G.resnet_generator(torch.cat([src_img * bg_mask, bg_mask], dim=1), sd, 'bg_model')
+    ft_mask = 1 - ref_morph(cond[:, -1:], 3, 'erode')
+    feats = G.encode_src(torch.cat([src_img * ft_mask, cond], dim=1), sd)
+    first_cam = tgt[0:1, 0:3]
+    worst = 0.0
+    for t in range(4):
+        th = tgt[t:t + 1]
+        cam = sinfo["cam"].clone()
+        cam[:, 1:] += th[:, 1:3] - first_cam[:, 1:]
+        tsf_theta = torch.cat([cam, th[:, 3:75], sinfo["shape"]], dim=1)
+        ref_verts = smpl_ref.get_details(m, tsf_theta)["verts"]
+        gpu_verts = body.get_details(tsf_theta.to(cuda))["verts"].cpu()
+        assert (gpu_verts - ref_verts).abs().max() < 1e-5
+        c = nmr_ref.correspond(cam, gpu_verts, f, tabs["map_fn"], p2v, src_img, size)
+        pred, _, _ = G.imitator_forward(bg, feats, c["tsf_inputs"], c["T"], sd)
+        worst = max(worst, np.abs(outs[t] - pred[0].permute(1, 2, 0).numpy()).max())
+    print("Imitator (SMPL LBS kernels) vs oracle loop: max-abs %.3e over 4 frames" % worst)
+    assert worst < 1e-3
+
+
+def _np_u8_bgr(frames_hwc):
+    """utils/cv_utils.py:23-36 with normalize=True, minus the imwrite: RGB->BGR, ((img+1)/2.0*255).astype(uint8)."""
+    img = frames_hwc[..., ::-1]
+    return ((img + 1) / 2.0 * 255).astype(np.uint8)
+
+
+def test_output_path_layouts(cuda):
+    """HWC float frames and BGR uint8 frames straight from the head kernel / lwb_frames_out."""
+    from impersonator_b200 import kernels as K
+    torch.set_grad_enabled(False)
+    g = torch.Generator().manual_seed(3)
+    frames = (torch.rand(3, 3, 64, 48, generator=g) * 2 - 1).to(cuda)
+    frames[0, :, 0, 0] = torch.tensor([-1.0, 1.0, 0.0])
+    hwc, u8 = K.frames_out(frames, want_hwc=True, want_u8=True)
+    ref = frames.permute(0, 2, 3, 1).cpu().numpy()
+    assert np.array_equal(hwc.cpu().numpy(), ref)
+    assert np.array_equal(u8.cpu().numpy(), _np_u8_bgr(ref))
+    raw = torch.randn(2, 32, 32, 4, generator=g).to(cuda)
+    bg = (torch.rand(1, 3, 32, 32, generator=g) * 2 - 1).to(cuda)
+    p_hwc = torch.empty(2, 32, 32, 3, device=cuda)
+    p_u8 = torch.empty(2, 32, 32, 3, dtype=torch.uint8, device=cuda)
+    color, mask, pred = K.heads_composite(raw, bg, pred_hwc=p_hwc, pred_u8=p_u8)
+    assert torch.equal(p_hwc, pred.permute(0, 2, 3, 1))
+    assert np.array_equal(p_u8.cpu().numpy(), _np_u8_bgr(p_hwc.cpu().numpy()))
+
+
+def test_imitator_uint8_and_saved_frames(cuda, tmp_path):
+    torch.set_grad_enabled(False)
+    size = 256
+    v, f = S.uv_sphere()
+    tabs = S.synthetic_tables()
+    net = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=0))
+    render = SMPLRenderer(image_size=size, faces=f.numpy(), map_fn=tabs["map_fn"], has_front=True,
+                          front_map_fn=tabs["front_map_fn"], back_map_fn=tabs["back_map_fn"])
+    for front in (False, True):
+        opt = Opt()
+        opt.front_warp = front
+        im = Imitator(opt, generator=net, hmr=SyntheticBodyModel(v), render=render, device=cuda)
+        src_theta = np.zeros(85, np.float32)
+        src_theta[0] = 0.95
+        im.personalize("", src_smpl=src_theta, src_img=S.synthetic_source(size))
+        tgt = np.zeros((3, 85), np.float32)
+        tgt[:, 0], tgt[:, 3] = 0.9, np.array([0.2, 1.0, -2.0])
+        floats = im.inference_by_smpls(list(tgt))
+        u8 = im.inference_by_smpls(list(tgt), as_uint8=True)
+        assert u8[0].dtype == np.uint8 and u8[0].shape == (size, size, 3)
+        for a, b in zip(floats, u8):
+            assert np.array_equal(_np_u8_bgr(a), b)
+        try:
+            import cv2
+        except ImportError:
+            continue
+        out = im.inference_by_smpls(list(tgt), output_dir=str(tmp_path))
+        assert np.array_equal(out[1], floats[1])
+        saved = cv2.imread(str(tmp_path / ("pred_%.8d.jpg" % 1)))
+        assert saved is not None and saved.shape == (size, size, 3)
+        assert np.abs(saved.astype(np.int32) - u8[1].astype(np.int32)).mean() < 20     # JPEG round trip
