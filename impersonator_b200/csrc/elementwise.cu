@@ -103,9 +103,24 @@ __global__ void __launch_bounds__(256) k_nhwc_to_nchw(
 }
 
 // ---------------------------------------------------------------------------------------------
-// InstanceNorm statistics: (sum, sumsq) in f64 come out of the conv epilogue (or k_stats_nhwc) and are
-// turned into y = x*scale + shift inside k_norm_act (biased variance, eps inside the sqrt).
+// InstanceNorm statistics (sum, sumsq in f64 from the conv epilogue) -> per-(n,c) scale/shift
+//   y = gamma*(x-mean)*rstd + beta = x*scale + shift        (biased variance, eps inside the sqrt)
 // ---------------------------------------------------------------------------------------------
+__global__ void k_finalize_stats(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, int n, int c, double inv_hw,
+                                 float2* __restrict__ ss)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    const int ch = i % c;
+    const double mean = stats[2 * i] * inv_hw;
+    double var = stats[2 * i + 1] * inv_hw - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
+    ss[i] = make_float2(g * rstd, bt - (float)mean * g * rstd);
+}
+
 // Plain (two-pass, fp64) statistics for tensors that did not come out of the conv epilogue.
 __global__ void __launch_bounds__(256) k_stats_nhwc(const float* __restrict__ x, int hw, int c, double* __restrict__ stats)
 {
@@ -136,7 +151,7 @@ __global__ void __launch_bounds__(256) k_stats_nhwc(const float* __restrict__ x,
 // one thread = one pixel x 8 channels (32B fp32 loads, 16B fp16 stores)
 // ---------------------------------------------------------------------------------------------
 struct NormActParams {
-    const float* raw; const double* stats; const float* gamma; const float* beta; float eps; double inv_hw; int relu;
+    const float* raw; const float2* ss; int relu;
     int n, h, w, c;
     const float* residual;
     const float* warp_src; int src_batch; const float* T; int th, tw, align_corners;
@@ -200,33 +215,17 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
             res[r][0] = a.x; res[r][1] = a.y; res[r][2] = a.z; res[r][3] = a.w; res[r][4] = c.x; res[r][5] = c.y; res[r][6] = c.z; res[r][7] = c.w;
         }
     }
-    if (P.stats) {
-        // finalize the epilogue's f64 (sum, sumsq) in place: no separate scale/shift kernel.  Variance in f64
-        // (cancellation), the rest in f32.  Both rounds of a thread share the batch index except at a seam.
-        static_assert(R == 2, "two rounds");
-        const bool same = bb[1] == bb[0];
-#pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-            if (pass == 1 && same) break;
-            const double2* st = reinterpret_cast<const double2*>(P.stats) + (size_t)bb[pass] * P.c + g * 8;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const double2 sq = __ldg(st + k);
-                const double mean = sq.x * P.inv_hw;
-                const float var = fmaxf((float)(sq.y * P.inv_hw - mean * mean), 0.f);
-                const float gr = (P.gamma ? __ldg(P.gamma + g * 8 + k) : 1.f) * (1.f / sqrtf(var + P.eps));
-                const float sf = (P.beta ? __ldg(P.beta + g * 8 + k) : 0.f) - (float)mean * gr;
-                if (pass == 0) {
-                    v[0][k] = fmaf(v[0][k], gr, sf);
-                    if (same) v[1][k] = fmaf(v[1][k], gr, sf);
-                } else {
-                    v[1][k] = fmaf(v[1][k], gr, sf);
-                }
-            }
-        }
-    }
 #pragma unroll
     for (int r = 0; r < R; r++) {
+        if (P.ss) {
+            const float4* ss = reinterpret_cast<const float4*>(P.ss + (size_t)bb[r] * P.c + g * 8);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 s2 = __ldg(ss + k);         // (scale, shift) of channels 2k, 2k+1
+                v[r][2 * k] = fmaf(v[r][2 * k], s2.x, s2.y);
+                v[r][2 * k + 1] = fmaf(v[r][2 * k + 1], s2.z, s2.w);
+            }
+        }
         if (P.relu) {
 #pragma unroll
             for (int k = 0; k < 8; k++) v[r][k] = fmaxf(v[r][k], 0.f);
@@ -420,11 +419,16 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
 {
     LWB_CHECK_ARG(raw, "null pointer");
     LWB_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0, "channels must be a multiple of 8");
-    (void)scale_shift_ws;                                 // kept in the ABI; the finalize now runs inside k_norm_act
+    LWB_CHECK_ARG(!stats || scale_shift_ws, "stats needs the scale/shift workspace [n,c,2] f32");
     LWB_CHECK_ARG(!warp_src || (T && th > 0 && tw > 0 && (src_batch == 1 || src_batch == n)), "bad warp arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    if (stats) {
+        k_finalize_stats<<<lwb::ceil_div((long)n * c, 256), 256, 0, st>>>(
+            stats, gamma, beta, eps, n, c, 1.0 / ((double)h * w), (float2*)scale_shift_ws);
+        LWB_LAUNCH_OK();
+    }
     NormActParams P;
-    P.raw = raw; P.stats = stats; P.gamma = gamma; P.beta = beta; P.eps = eps; P.inv_hw = 1.0 / ((double)h * w); P.relu = relu;
+    P.raw = raw; P.ss = stats ? (const float2*)scale_shift_ws : nullptr; P.relu = relu;
     P.n = n; P.h = h; P.w = w; P.c = c;
     P.residual = residual;
     P.warp_src = warp_src; P.src_batch = src_batch; P.T = T; P.th = th; P.tw = tw; P.align_corners = align_corners;

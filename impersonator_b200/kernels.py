@@ -278,7 +278,7 @@ def norm_act_nhwc(raw, stats, gamma, beta, relu, ws, eps=1e-5, residual=None, wa
     if warp_src is not None:
         sb = warp_src.shape[0]
         th, tw = T.shape[1:3]
-    _count(1)
+    _count(2 if stats is not None else 1)
     per = 4 + (4 if residual is not None else 0) + (4 if y_f32 is not None else 0) \
         + (2 if y_hi is not None else 0) + (2 if y_lo is not None else 0)
     nbytes = n * h * w * c * per + (warp_src.numel() * 4 + n * h * w * 8 if warp_src is not None else 0)

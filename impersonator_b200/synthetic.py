@@ -193,19 +193,28 @@ def synthetic_smpl_model(seed=3, num_betas=10, num_joints=19):
             m[j, idx] = w / w.sum()
         return sp.csc_matrix(m)
 
-    weights = np.zeros((V, 24), dtype=np.float64)
-    for k, off in enumerate((0, -1, 1, 2)):
-        j = np.clip(band + off, 0, 23)
-        weights[np.arange(V), j] += (0.55, 0.2, 0.15, 0.1)[k] * (0.5 + rs.rand(V))
+    # smooth skinning weights: a Gaussian over the (continuous) height coordinate, 4 nearest joints kept
+    t = np.empty(V, dtype=np.float64)
+    t[order] = (np.arange(V) + 0.5) * 24.0 / V - 0.5
+    weights = np.exp(-0.5 * ((t[:, None] - np.arange(24)[None, :]) / 0.8) ** 2)
+    kth = np.sort(weights, axis=1)[:, -4][:, None]
+    weights = np.where(weights >= kth, weights, 0.0)
     weights /= weights.sum(axis=1, keepdims=True)
+    # smooth (low-frequency) blend shapes: 12 basis functions of the vertex position, random mixing
+    ang = np.arctan2(v[:, 2], v[:, 0])
+    basis = np.stack([np.ones(V), v[:, 1], v[:, 1] ** 2, np.sin(3 * v[:, 1]), np.cos(3 * v[:, 1]), np.sin(ang), np.cos(ang),
+                      np.sin(2 * ang), np.cos(2 * ang), np.sin(ang) * v[:, 1], np.cos(ang) * v[:, 1], np.sin(6 * v[:, 1])], axis=1)
+
+    def smooth_dirs(n, scale):
+        return np.einsum('vi,idk->vdk', basis, rs.randn(basis.shape[1], 3, n)) * scale
     kintree = np.zeros((2, 24), dtype=np.uint32)
     kintree[0] = np.array(SMPL_PARENTS, dtype=np.int64).astype(np.uint32)
     kintree[1] = np.arange(24)
     return {
         "f": f.numpy().astype(np.uint32),
         "v_template": v,
-        "shapedirs": rs.randn(V, 3, num_betas) * 0.01,
-        "posedirs": rs.randn(V, 3, 207) * 0.004,
+        "shapedirs": smooth_dirs(num_betas, 0.004),
+        "posedirs": smooth_dirs(207, 0.0015),
         "J_regressor": banded(24, 40),
         "kintree_table": kintree,
         "weights": weights,
@@ -218,7 +227,7 @@ def synthetic_smpl_params(batch, seed=17):
     g = torch.Generator().manual_seed(seed)
     cam = torch.stack([0.8 + 0.3 * torch.rand(batch, generator=g), torch.rand(batch, generator=g) * 0.2 - 0.1,
                        torch.rand(batch, generator=g) * 0.2 - 0.1], dim=1)
-    pose = torch.randn(batch, 72, generator=g) * 0.25
+    pose = torch.randn(batch, 72, generator=g) * 0.1
     pose[:, 0:3] = torch.stack([torch.randn(batch, generator=g) * 0.2, (torch.rand(batch, generator=g) * 2 - 1) * math.pi,
                                 torch.randn(batch, generator=g) * 0.1], dim=1)
     shape = torch.randn(batch, 10, generator=g)

@@ -158,8 +158,7 @@ int lwb_instance_stats_nhwc(const float* x, int n, int h, int w, int c, double* 
  *   networks/generator.py:13-20 (ResidualBlock), :80-95 (encoders), :283-295 (the "+ warp" of the LWB).
  * raw [n,h,w,c] fp32; stats from the conv epilogue (nullable -> no normalisation); gamma/beta [c];
  * residual (nullable) [n,h,w,c] fp32; warp_src (nullable) [src_batch,h,w,c] fp32 NHWC sampled at
- * T [n,TH,TW,2] resized to (h,w) (generator.py:303-320).  scale_shift_ws: unused since the finalize moved
- * into the kernel (kept for ABI stability; may be NULL).
+ * T [n,TH,TW,2] resized to (h,w) (generator.py:303-320).  scale_shift_ws: [n,c,2] f32 scratch.
  * Outputs (each nullable): y_f32 [n,h,w,c]; y_hi / y_lo fp16 [n,h,w,c].  c % 8 == 0. */
 int lwb_norm_act_nhwc(const float* raw, const double* stats, const float* gamma, const float* beta,
                       float eps, int relu, int n, int h, int w, int c,
