@@ -40,6 +40,7 @@ SIGNATURES = {
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lwb_warp_nchw": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "lwb_pack_conv_weight": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lwb_pack_conv_weight_f8": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lwb_pack_conv_weight_rowk": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lwb_nchw_to_nhwc_split": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lwb_nhwc_to_nchw": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -51,7 +52,7 @@ SIGNATURES = {
     "lwb_conv2d_nhwc": (_i, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lwb_instance_stats_nhwc": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "lwb_norm_act_nhwc": (_i, [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i,
-                               _vp, _vp, _vp, _vp, _vp]),
+                               _vp, _vp, _vp, _vp, _i, _vp]),
     "lwb_pack_head_weights": (_i, [_vp, _vp, _vp, _vp]),
     "lwb_conv7x7_heads_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "lwb_heads_composite": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

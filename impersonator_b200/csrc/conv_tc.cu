@@ -58,6 +58,8 @@ struct ConvParams {
     int oy_mul, oy_add, ox_mul, ox_add;
     double* stats;
     int stages;                       // pipeline depth actually used (<= Cfg::STAGES; LWB_STAGES, diagnostic)
+    int f8;                           // SPLIT stages hold [A_hi | A_lo8 | B_hi | B_lo8]: 1 f16 + 1 f8f6f4 MMA per K step
+    float out_scale;                  // accumulator -> output (2^-15 in f8 mode, else 1)
 };
 
 template <int N_TILE, bool SPLIT, int KC = KCHUNK>
@@ -151,6 +153,13 @@ __device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Same instruction on 8-bit operands (E4M3 x E4M3: the format fields of the instruction descriptor are both 0, like
+// F16 x F16): K = 32 per instruction, i.e. the same 32 B descriptor step, at twice the fp16 rate.
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -272,6 +281,10 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
                     r[j] = __float_as_uint(__uint_as_float(r[j]) + (__uint_as_float(r1[j]) + __uint_as_float(r2[j])));
             }
             tmem_ld_wait();
+            if (P.out_scale != 1.f) {
+#pragma unroll
+                for (int j = 0; j < CW; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * P.out_scale);
+            }
             if (valid && P.out) {
                 float4* o = reinterpret_cast<float4*>(optr + c * CW);
 #pragma unroll
@@ -425,7 +438,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
                             const uint64_t da = make_desc_k<KC>(a_hi + k * 32), db = make_desc_k<KC>(b_hi + k * 32);
                             const uint32_t first = (s > 0 || k > 0) ? 1u : 0u;
                             umma_f16(d_tmem, da, db, idesc, first);
-                            if (SPLIT) {
+                            if (SPLIT && P.f8) {
+                                umma_f8(d_tmem, make_desc_k<KC>(a_lo + k * 32), make_desc_k<KC>(b_lo + k * 32), idesc, 1u);
+                            } else if (SPLIT) {
                                 constexpr uint32_t A1 = C::NACC > 1 ? N_TILE : 0, A2 = C::NACC > 1 ? 2 * N_TILE : 0;
                                 umma_f16(d_tmem + A1, da, make_desc_k<KC>(b_lo + k * 32), idesc, C::NACC > 1 ? first : 1u);
                                 umma_f16(d_tmem + A2, make_desc_k<KC>(a_lo + k * 32), db, idesc, C::NACC > 1 ? first : 1u);
@@ -490,6 +505,11 @@ __device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, void* ds
 __device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f8_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
@@ -592,7 +612,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2(const __grid_consta
                         for (int k = 0; k < KCHUNK / 16; k++) {
                             const uint64_t da = make_desc(a_hi + k * 32), db = make_desc(b_hi + k * 32);
                             umma_f16_2sm(d_tmem, da, db, idesc, (s > 0 || k > 0) ? 1u : 0u);
-                            if (SPLIT) {
+                            if (SPLIT && P.f8) {
+                                umma_f8_2sm(d_tmem, make_desc(a_lo + k * 32), make_desc(b_lo + k * 32), idesc, 1u);
+                            } else if (SPLIT) {
                                 umma_f16_2sm(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
                                 umma_f16_2sm(d_tmem, make_desc(a_lo + k * 32), db, idesc, 1u);
                             }
@@ -655,6 +677,7 @@ struct HaloParams {
     float* out; int out_h, out_w, cout;
     int oy_mul, oy_add, ox_mul, ox_add;
     double* stats;
+    float out_scale;                  // always 1 (shared epilogue)
 };
 
 constexpr int HALO_NA = 2;            // activation ring depth
@@ -1028,7 +1051,10 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
 {
     LWB_CHECK_ARG(d && x0_hi && w_hi && out_raw && plan_out, "null pointer");
     const bool split = d->split != 0;
+    const bool f8 = d->split == 2;     // lo operands are fp8 pairs (lwb_pack_conv_weight_f8 / lo_format 1 of lwb_norm_act_nhwc)
+    LWB_CHECK_ARG(d->split >= 0 && d->split <= 2, "split must be 0, 1 or 2");
     LWB_CHECK_ARG(!split || (x0_lo && w_lo), "split mode needs the lo operands");
+    LWB_CHECK_ARG(!f8 || (!d->rowk && !d->halo), "the fp8 lo mode is not available for row-K / halo plans");
     LWB_CHECK_ARG(d->n > 0 && d->h_in > 0 && d->w_in > 0 && d->cout > 0, "non-positive size");
     LWB_CHECK_ARG(d->cout % 16 == 0, "cout must be a multiple of 16");
     int n_tile = pick_n_tile(d->cout, split, d->n_tile);
@@ -1056,7 +1082,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     if (two_sm) cl = 2;
     // K elements per pipeline stage: 64 (128 B rows, SWIZZLE_128B) or 32 (64 B rows, SWIZZLE_64B: twice the stages)
     int kc = KCHUNK;
-    { const char* e = getenv("LWB_KC"); if (e && atoi(e) == 32 && !d->rowk && !d->halo) { kc = 32; cl = 1; two_sm = false; } }
+    { const char* e = getenv("LWB_KC"); if (e && atoi(e) == 32 && !d->rowk && !d->halo && !f8) { kc = 32; cl = 1; two_sm = false; } }
 
     lwb_conv_plan* plan = new (std::nothrow) lwb_conv_plan();
     LWB_CHECK_ARG(plan, "out of host memory");
@@ -1073,6 +1099,8 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         if (getenv("LWB_DEBUG_NOEPI")) { p.oy_mul = -1; }
         p.out = getenv("LWB_DEBUG_NOSTORE") ? nullptr : out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
+        p.f8 = f8 ? 1 : 0;
+        p.out_scale = f8 ? (1.f / 32768.f) : 1.f;      // weights are packed x 2^15 in f8 mode (lwb_pack_conv_weight_f8)
         L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl; L.kc = d->rowk ? KCHUNK : kc;
         L.two_sm = two_sm;
         p.stages = 64;      // clamped to Cfg::STAGES at launch
@@ -1151,6 +1179,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         h.out = out_raw; h.out_h = d->h_out; h.out_w = d->w_out; h.cout = d->cout;
         h.oy_mul = 1; h.ox_mul = 1; h.oy_add = 0; h.ox_add = 0;
         h.stats = stats;
+        h.out_scale = 1.f;
         L.n_tile = n_tile; L.split = split; L.cl = 1; L.two_sm = false;
         const long total = (long)h.n_img * h.tiles_y * h.tiles_x * h.n_tiles_n;
         L.grid = (int)(total < sms ? total : sms);

@@ -3,6 +3,8 @@
 //
 // networks/generator.py:8-20 (ResidualBlock), :80-95 (Conv+IN+ReLU), :283-295 (tsf + warp),
 // :183-184 (tanh / sigmoid heads), models/imitator.py:330-331 (composite).
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "sample.cuh"
 
@@ -31,6 +33,42 @@ __global__ void k_pack_weight(const float* __restrict__ w, int cout, int cin, in
         split_half(v, h, l);
         hi[i] = h;
         if (lo) lo[i] = l;
+    }
+}
+
+// fp8 scales of the "fp16 + fp8" operand split (conv_tc.cu, f8 mode).  With hi = fp16(v), lo = v - hi:
+//     x * w ~= x_hi * w_hi + x * w_lo + x_lo * w            (the two small products only need ~4 bits)
+// and everything is accumulated 2^15 too large so that no fp8 operand underflows:
+//     A_hi = x_hi                 B_hi  = fp16(w_hi * 2^15)
+//     A_lo8[0:64]  = e4m3(x)      B_lo8[0:64]  = e4m3(w_lo * 2^15)
+//     A_lo8[64:128] = e4m3(x_lo * 2^12)   B_lo8[64:128] = e4m3(w * 2^3)
+// per 64-channel block (one 128 B K row); the epilogue multiplies by 2^-15.
+constexpr float kF8WScale = 32768.f, kF8XLoScale = 4096.f, kF8WHiScale = 8.f;
+
+__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+
+// weights, f8 mode: hi [tap][cout_pad][cin_pad] fp16 = w_hi * 2^15;  lo8: the same 2 bytes per element, per 64-channel
+// block [64 x e4m3(w_lo * 2^15)][64 x e4m3(w * 2^3)]
+__global__ void k_pack_weight_f8(const float* __restrict__ w, int cout, int cin, int kh, int kw, int transposed,
+                                 int cout_pad, int cin_pad, __half* __restrict__ hi, uint8_t* __restrict__ lo8)
+{
+    const long total = (long)kh * kw * cout_pad * cin_pad;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin_pad);
+        const int co = (int)((i / cin_pad) % cout_pad);
+        const int tap = (int)(i / ((long)cin_pad * cout_pad));
+        float v = 0.f;
+        if (ci < cin && co < cout) {
+            const int ky = tap / kw, kx = tap % kw;
+            v = transposed ? w[(((size_t)ci * cout + co) * kh + ky) * kw + kx]
+                           : w[(((size_t)co * cin + ci) * kh + ky) * kw + kx];
+        }
+        const __half h = __float2half_rn(v);
+        const float lo = v - __half2float(h);
+        hi[i] = __float2half_rn(__half2float(h) * kF8WScale);          // exact unless |w| >= 2 (checked on the host side)
+        uint8_t* blk = lo8 + (i - ci) * 2 + (size_t)(ci / 64) * 128;
+        blk[ci % 64] = to_e4m3(lo * kF8WScale);
+        blk[64 + ci % 64] = to_e4m3(v * kF8WHiScale);
     }
 }
 
@@ -156,6 +194,7 @@ struct NormActParams {
     const float* residual;
     const float* warp_src; int src_batch; const float* T; int th, tw, align_corners;
     float* y_f32; __half* y_hi; __half* y_lo;
+    int lo_format;                                       // 0: y_lo = fp16 residual; 1: fp8 pair blocks (see kF8* above)
 };
 
 // Block = 256 threads = (256 / groups) pixels x groups channel-octets, two pixel rounds per thread so
@@ -264,7 +303,22 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
 #pragma unroll
             for (int k = 0; k < 8; k++) split_half(v[r][k], hh[k], ll[k]);
             *reinterpret_cast<uint4*>(P.y_hi + off[r]) = *reinterpret_cast<const uint4*>(hh);
-            if (P.y_lo) *reinterpret_cast<uint4*>(P.y_lo + off[r]) = *reinterpret_cast<const uint4*>(ll);
+            if (P.y_lo && P.lo_format == 0) {
+                *reinterpret_cast<uint4*>(P.y_lo + off[r]) = *reinterpret_cast<const uint4*>(ll);
+            } else if (P.y_lo) {
+                __align__(8) uint8_t x8[8];
+                __align__(8) uint8_t l8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    x8[k] = to_e4m3(v[r][k]);
+                    l8[k] = to_e4m3((v[r][k] - __half2float(hh[k])) * kF8XLoScale);
+                }
+                // channel c of this pixel lives in 64-channel block c / 64: bytes [c % 64] and [64 + c % 64]
+                const int ch = g * 8;
+                uint8_t* blk = reinterpret_cast<uint8_t*>(P.y_lo) + (off[r] - ch) * 2 + (size_t)(ch / 64) * 128 + (ch % 64);
+                *reinterpret_cast<uint2*>(blk) = *reinterpret_cast<const uint2*>(x8);
+                *reinterpret_cast<uint2*>(blk + 64) = *reinterpret_cast<const uint2*>(l8);
+            }
         }
     }
 }
@@ -363,6 +417,18 @@ extern "C" int lwb_pack_conv_weight(const float* w, int cout, int cin, int kh, i
     return LWB_OK;
 }
 
+extern "C" int lwb_pack_conv_weight_f8(const float* w, int cout, int cin, int kh, int kw, int transposed,
+                                       int cout_pad, int cin_pad, uint16_t* w_hi, uint8_t* w_lo8, lwb_stream_t stream)
+{
+    LWB_CHECK_ARG(w && w_hi && w_lo8, "null pointer");
+    LWB_CHECK_ARG(cout > 0 && cin > 0 && kh > 0 && kw > 0 && cout_pad >= cout && cin_pad >= cin && (cin_pad % 64) == 0, "bad sizes");
+    const long total = (long)kh * kw * cout_pad * cin_pad;
+    k_pack_weight_f8<<<(int)min((total + 255) / 256, 4096l), 256, 0, (cudaStream_t)stream>>>(
+        w, cout, cin, kh, kw, transposed, cout_pad, cin_pad, (__half*)w_hi, w_lo8);
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
 extern "C" int lwb_pack_conv_weight_rowk(const float* w, int cout, int cin, int kh, int kw,
                                          int cout_pad, int cpx, int kxs, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream)
 {
@@ -415,8 +481,9 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
                                  const float* residual,
                                  const float* warp_src, int src_batch, const float* T, int th, int tw, int align_corners,
                                  float* scale_shift_ws,
-                                 float* y_f32, uint16_t* y_hi, uint16_t* y_lo, lwb_stream_t stream)
+                                 float* y_f32, uint16_t* y_hi, uint16_t* y_lo, int lo_format, lwb_stream_t stream)
 {
+    LWB_CHECK_ARG(lo_format == 0 || (lo_format == 1 && (c % 64) == 0), "lo_format 1 (fp8 pairs) needs channels in blocks of 64");
     LWB_CHECK_ARG(raw, "null pointer");
     LWB_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0, "channels must be a multiple of 8");
     LWB_CHECK_ARG(!stats || scale_shift_ws, "stats needs the scale/shift workspace [n,c,2] f32");
@@ -432,7 +499,7 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
     P.n = n; P.h = h; P.w = w; P.c = c;
     P.residual = residual;
     P.warp_src = warp_src; P.src_batch = src_batch; P.T = T; P.th = th; P.tw = tw; P.align_corners = align_corners;
-    P.y_f32 = y_f32; P.y_hi = (__half*)y_hi; P.y_lo = (__half*)y_lo;
+    P.y_f32 = y_f32; P.y_hi = (__half*)y_hi; P.y_lo = (__half*)y_lo; P.lo_format = lo_format;
     const int groups = c / 8;
     LWB_CHECK_ARG(groups <= 256 && 256 % groups == 0, "channels / 8 must divide 256");
     const long blocks = lwb::ceil_div((long)n * h * w, (256 / groups) * 2);

@@ -33,10 +33,15 @@ from ._lib import LwbError
 
 
 def _split_mode():
+    """LWB_PRECISION -> operand split code of the conv engine (lwb_conv_desc.split):
+    fp16x3 = 1: x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, all fp16 (3 MMAs per K step);
+    fp16f8 = 2: x_hi*w_hi in fp16 + (x*w_lo, x_lo*w) in e4m3 at twice the rate (2 MMA-equivalents per K step);
+    fp16   = 0: single pass (not parity-gated)."""
     mode = os.environ.get("LWB_PRECISION", "fp16x3")
-    if mode not in ("fp16x3", "fp16"):
-        raise LwbError("LWB_PRECISION must be fp16x3 or fp16")
-    return mode == "fp16x3"
+    codes = {"fp16": 0, "fp16x3": 1, "fp16f8": 2}
+    if mode not in codes:
+        raise LwbError("LWB_PRECISION must be fp16x3, fp16f8 or fp16")
+    return codes[mode]
 
 
 def _align_corners():
@@ -48,6 +53,8 @@ def _halo_mode():
     kernel for the row-K stem and the skippers + 7x7 heads on tensor cores; 'all' = also the residual blocks.
     The halo variant is correct (tests/test_conv_gpu.py) but measured 10-30% SLOWER than per-tap loads on B200
     and the N=16 tensor-core heads 3x slower than the CUDA-core kernel, hence the default."""
+    if os.environ.get("LWB_PRECISION", "fp16x3") == "fp16f8":
+        return '0'                                         # the halo kernel has no fp8 path
     return os.environ.get("LWB_HALO", "0")
 
 
@@ -149,9 +156,9 @@ class _StreamBase(object):
         L = _Layer()
         wt = (weight if weight is not None else conv.weight).detach()
         if rowk:
-            L.w = K.pack_conv_weight_rowk(wt, split=self.split)
+            L.w = K.pack_conv_weight_rowk(wt, split=min(self.split, 1))       # the stem keeps the fp16 hi/lo input
             cout, kh, kw = wt.shape[0], wt.shape[2], wt.shape[3]
-            d = K.make_conv_desc(self.B, h, w, 8, cout, kh, kw, stride=1, pad=kh // 2, split=self.split,
+            d = K.make_conv_desc(self.B, h, w, 8, cout, kh, kw, stride=1, pad=kh // 2, split=min(self.split, 1),
                                  rowk=True, row_pitch=row_pitch, halo=halo)
         else:
             L.w = K.pack_conv_weight(wt, transposed=transposed, split=self.split)
@@ -186,7 +193,7 @@ class _StreamBase(object):
     def _conv_norm(self, L, out, relu, residual=None, warp_src=None, T=None, ac=False):
         L.plan.run()
         K.norm_act_nhwc(L.raw, L.stats, L.gamma, L.beta, relu, self.ws, residual=residual, warp_src=warp_src, T=T,
-                        align_corners=ac, y_f32=out.f32, y_hi=out.hi, y_lo=out.lo)
+                        align_corners=ac, y_f32=out.f32, y_hi=out.hi, y_lo=out.lo, lo_format=1 if self.split == 2 else 0)
 
 
 class _UnetStream(_StreamBase):
@@ -279,7 +286,7 @@ class _UnetStream(_StreamBase):
         if act.f32 is None:
             raise LwbError("second warp needs an fp32 activation")
         K.norm_act_nhwc(act.f32, None, None, None, False, self.ws, warp_src=src, T=T, align_corners=ac,
-                        y_f32=act.f32, y_hi=act.hi, y_lo=act.lo)
+                        y_f32=act.f32, y_hi=act.hi, y_lo=act.lo, lo_format=1 if self.split == 2 else 0)
 
     def resnets(self, warp_srcs=None, T=None, ac=False):
         x = self.e[self.n_down]

@@ -151,8 +151,11 @@ def warp_nchw(x, T, align_corners=False, out=None, accumulate=False):
 
 
 def pack_conv_weight(w, transposed=False, cout_pad=None, cin_pad=None, split=True):
-    """OIHW / IOHW fp32 -> ([tap][cout_pad][cin_pad] fp16 hi, lo)."""
+    """OIHW / IOHW fp32 -> ([tap][cout_pad][cin_pad] fp16 hi, lo).  split: 0/False single, 1/True fp16 hi+lo,
+    2 fp16 hi (x 2^15) + fp8 pair blocks (lwb_pack_conv_weight_f8)."""
     _chk_cuda(w)
+    if int(split) == 2:
+        return _pack_conv_weight_f8(w, transposed, cout_pad, cin_pad)
     w = w.float().contiguous()
     if transposed:
         cin, cout, kh, kw = w.shape
@@ -164,6 +167,23 @@ def pack_conv_weight(w, transposed=False, cout_pad=None, cin_pad=None, split=Tru
     lo = torch.empty_like(hi) if split else None
     check(lib().lwb_pack_conv_weight(ptr(w), cout, cin, kh, kw, 1 if transposed else 0, cout_pad, cin_pad,
                                      ptr(hi), ptr(lo), stream()), "lwb_pack_conv_weight")
+    return hi, lo
+
+
+def _pack_conv_weight_f8(w, transposed, cout_pad, cin_pad):
+    w = w.float().contiguous()
+    if transposed:
+        cin, cout, kh, kw = w.shape
+    else:
+        cout, cin, kh, kw = w.shape
+    cout_pad = cout_pad or cout
+    cin_pad = cin_pad or cin
+    if float(w.abs().max()) >= 1.99:
+        raise LwbError("fp16f8 mode packs weights x 2^15 in fp16: |w| must stay below 2 (use LWB_PRECISION=fp16x3)")
+    hi = torch.empty((kh * kw, cout_pad, cin_pad), dtype=torch.float16, device=w.device)
+    lo = torch.empty_like(hi)                                   # same bytes, fp8 pair blocks inside
+    check(lib().lwb_pack_conv_weight_f8(ptr(w), cout, cin, kh, kw, 1 if transposed else 0, cout_pad, cin_pad,
+                                        ptr(hi), ptr(lo), stream()), "lwb_pack_conv_weight_f8")
     return hi, lo
 
 
@@ -256,7 +276,7 @@ def make_conv_desc(n, h_in, w_in, cin0, cout, kh, kw, stride=1, pad=0, dil=1, ci
         w_out = (w_in + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     return ConvDesc(n=n, h_in=h_in, w_in=w_in, h_out=h_out, w_out=w_out, cin0=cin0, cin1=cin1, cout=cout,
                     kh=kh, kw=kw, stride=stride, pad=pad, dil=dil, transposed=1 if transposed else 0,
-                    split=1 if split else 0, rowk=1 if rowk else 0, row_pitch=row_pitch, n_tile=n_tile,
+                    split=int(split), rowk=1 if rowk else 0, row_pitch=row_pitch, n_tile=n_tile,
                     halo=1 if halo else 0)
 
 
@@ -270,8 +290,9 @@ def instance_stats_nhwc(x, stats=None):
 
 
 def norm_act_nhwc(raw, stats, gamma, beta, relu, ws, eps=1e-5, residual=None, warp_src=None, T=None,
-                  align_corners=False, y_f32=None, y_hi=None, y_lo=None):
-    """InstanceNorm + ReLU + residual + LWB warp-add on an NHWC fp32 tensor (lwb_norm_act_nhwc)."""
+                  align_corners=False, y_f32=None, y_hi=None, y_lo=None, lo_format=0):
+    """InstanceNorm + ReLU + residual + LWB warp-add on an NHWC fp32 tensor (lwb_norm_act_nhwc).
+    lo_format 1: y_lo receives the fp8 pair blocks that split=2 conv plans consume."""
     _chk_cuda(raw, stats, gamma, beta, residual, warp_src, T, ws, y_f32, y_hi, y_lo)
     n, h, w, c = raw.shape
     sb, th, tw = 0, 0, 0
@@ -285,7 +306,7 @@ def norm_act_nhwc(raw, stats, gamma, beta, relu, ws, eps=1e-5, residual=None, wa
     with _Prof("norm", nbytes, "%dx%d c%d%s%s" % (h, w, c, " +res" if residual is not None else "", " +warp" if warp_src is not None else "")):
         check(lib().lwb_norm_act_nhwc(ptr(raw), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if relu else 0, n, h, w, c,
                                       ptr(residual), ptr(warp_src), sb, ptr(T), th, tw, 1 if align_corners else 0,
-                                      ptr(ws), ptr(y_f32), ptr(y_hi), ptr(y_lo), stream()), "lwb_norm_act_nhwc")
+                                      ptr(ws), ptr(y_f32), ptr(y_hi), ptr(y_lo), int(lo_format), stream()), "lwb_norm_act_nhwc")
 
 
 def pack_head_weights(w_img, w_att):

@@ -102,6 +102,12 @@ int lwb_warp_nchw(const float* x, int src_batch, int channels, int h, int w,
  * engine's [tap][Cout_pad][Cin_pad] fp16 hi/lo layout (done once at load time). w_lo nullable. */
 int lwb_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int transposed,
                          int cout_pad, int cin_pad, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream);
+/* Weights for the "fp16 + fp8" operand split (lwb_conv_desc.split = 2): w_hi [taps][cout_pad][cin_pad] fp16 holds
+ * fp16(w) * 2^15; w_lo8 (same byte size) holds, per 64-input-channel block of 128 bytes, 64 x e4m3((w - fp16(w)) * 2^15)
+ * followed by 64 x e4m3(w * 2^3).  |w| must stay below 2.  cin_pad % 64 == 0.  See DESIGN.md section 4. */
+int lwb_pack_conv_weight_f8(const float* w, int cout, int cin, int kh, int kw, int transposed,
+                            int cout_pad, int cin_pad, uint16_t* w_hi, uint8_t* w_lo8, lwb_stream_t stream);
+
 /* Row-K packing for the 7x7 stem: [ky][cout_pad][kxs*cpx], K index = kx*cpx + c (zero beyond kw / cin). */
 int lwb_pack_conv_weight_rowk(const float* w, int cout, int cin, int kh, int kw,
                               int cout_pad, int cpx, int kxs, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream);
@@ -121,7 +127,8 @@ typedef struct lwb_conv_desc {
     int cout;                 /* multiple of 16 */
     int kh, kw, stride, pad, dil;
     int transposed;           /* ConvTranspose2d(k=3, s=2, p=1, output_padding=1) when != 0 */
-    int split;                /* 1 = 3-pass fp16 split (parity mode), 0 = single pass ("fast") */
+    int split;                /* 1 = 3-pass fp16 split (parity mode), 0 = single pass ("fast"), 2 = fp16 main product +
+                                 both small products in fp8 (lo operands from lwb_pack_conv_weight_f8 / lo_format 1) */
     int rowk;                 /* 1 = 7x7-stem row-K mode: input is a padded NHWC8 buffer (see conv_tc.cu) */
     int row_pitch;            /* rowk: pixels per padded row (>= w_in + 8) */
     int n_tile;               /* 0 = auto; else force the N tile (16/64/128/256, must divide cout) */
@@ -159,13 +166,15 @@ int lwb_instance_stats_nhwc(const float* x, int n, int h, int w, int c, double* 
  * raw [n,h,w,c] fp32; stats from the conv epilogue (nullable -> no normalisation); gamma/beta [c];
  * residual (nullable) [n,h,w,c] fp32; warp_src (nullable) [src_batch,h,w,c] fp32 NHWC sampled at
  * T [n,TH,TW,2] resized to (h,w) (generator.py:303-320).  scale_shift_ws: [n,c,2] f32 scratch.
- * Outputs (each nullable): y_f32 [n,h,w,c]; y_hi / y_lo fp16 [n,h,w,c].  c % 8 == 0. */
+ * Outputs (each nullable): y_f32 [n,h,w,c]; y_hi / y_lo fp16 [n,h,w,c].  c % 8 == 0.
+ * lo_format 0: y_lo = fp16(y - y_hi).  lo_format 1 (c % 64 == 0; consumers are split = 2 conv plans): y_lo holds, per
+ * pixel and 64-channel block of 128 bytes, 64 x e4m3(y) followed by 64 x e4m3((y - y_hi) * 2^12). */
 int lwb_norm_act_nhwc(const float* raw, const double* stats, const float* gamma, const float* beta,
                       float eps, int relu, int n, int h, int w, int c,
                       const float* residual,
                       const float* warp_src, int src_batch, const float* T, int th, int tw, int align_corners,
                       float* scale_shift_ws,
-                      float* y_f32, uint16_t* y_hi, uint16_t* y_lo, lwb_stream_t stream);
+                      float* y_f32, uint16_t* y_hi, uint16_t* y_lo, int lo_format, lwb_stream_t stream);
 
 /* 7x7 output heads of the generator (networks/generator.py:126-134): img_reg (64->3) and
  * attetion_reg (64->1) as ONE 64->4 convolution, x [n,h,w,64] fp32 NHWC, w4 [49][64][4] fp32

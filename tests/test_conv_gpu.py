@@ -30,8 +30,11 @@ def report(name, got, ref):
 def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x1=None, n_tile=0, stats=True, halo=False):
     """x [n,c,h,w] fp32 CPU, w OIHW (or IOHW when transposed) -> NCHW fp32 CPU result, stats."""
     n, c0, h, wd = x.shape
-    xs = K.nchw_to_nhwc_split(x.to(cuda), split=split)
-    x1s = K.nchw_to_nhwc_split(x1.to(cuda), split=split) if x1 is not None else None
+    if int(split) == 2:
+        xs, x1s = to_f8_operands(cuda, x), (to_f8_operands(cuda, x1) if x1 is not None else None)
+    else:
+        xs = K.nchw_to_nhwc_split(x.to(cuda), split=split)
+        x1s = K.nchw_to_nhwc_split(x1.to(cuda), split=split) if x1 is not None else None
     ws = K.pack_conv_weight(w.to(cuda), transposed=transposed, split=split)
     cout = w.shape[1] if transposed else w.shape[0]
     kh, kw = w.shape[2:]
@@ -44,6 +47,30 @@ def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x
     plan.run()
     torch.cuda.synchronize()
     return K.nhwc_to_nchw(out).cpu(), (st.cpu() if stats else None)
+
+
+def to_f8_operands(cuda, x):
+    """NCHW fp32 -> (hi fp16 NHWC, fp8 pair blocks) through the norm kernel used as a plain converter."""
+    raw = x.permute(0, 2, 3, 1).contiguous().to(cuda)
+    hi = torch.empty(raw.shape, dtype=torch.float16, device=cuda)
+    lo = torch.empty_like(hi)
+    K.norm_act_nhwc(raw, None, None, None, False, None, y_hi=hi, y_lo=lo, lo_format=1)
+    return hi, lo
+
+
+def q8(t):
+    return t.clamp(-448, 448).to(torch.float8_e4m3fn).double()
+
+
+def emulate_f8(x, w, conv):
+    """The arithmetic the fp16f8 mode is meant to perform, in float64 on the CPU."""
+    xh = x.half().double()
+    wh = w.half().double()
+    xl, wl = x.double() - xh, w.double() - wh
+    main = conv(xh, wh)
+    t2 = conv(q8(x), q8((wl * 32768).float())) / 32768
+    t3 = conv(q8((xl * 4096).float()), q8(w * 8)) / 32768
+    return (main + t2 + t3).float()
 
 
 def check_stats(st, ref):
@@ -225,3 +252,38 @@ def test_direct_conv(cuda):
         ref = F.conv2d(x, wt, b, stride=s, padding=p, dilation=d)
         got = K.conv2d_direct_nchw(x.to(cuda), wt.to(cuda), b.to(cuda), stride=s, pad=p, dil=d).cpu()
         assert report("direct k%d s%d d%d" % (k, s, d), got, ref) < 1e-5
+
+
+F8_CASES = [c for c in CASES if c[2] % 64 == 0 and c[9] != 16]
+
+
+@pytest.mark.parametrize("case", F8_CASES, ids=[c[0] for c in F8_CASES])
+def test_conv2d_fp16f8(cuda, case):
+    """split = 2: x_hi*w_hi on the fp16 path + (x*w_lo, x_lo*w) as e4m3 MMAs into the same accumulator."""
+    name, n, cin, cout, h, w, k, stride, pad, n_tile = case
+    x = rnd(n, cin, h, w, seed=1)
+    wt = rnd(cout, cin, k, k, seed=2, scale=0.05)
+    ref = F.conv2d(x, wt, stride=stride, padding=pad)
+    got, st = run_conv(cuda, x, wt, stride=stride, pad=pad, split=2, n_tile=n_tile)
+    rel = report(name + "/fp16f8 vs fp32", got, ref)
+    assert rel < 3e-4
+    emu = emulate_f8(x, wt, lambda a, b: F.conv2d(a, b, stride=stride, padding=pad))
+    rel_e = report(name + "/fp16f8 vs its float64 emulation", got, emu)
+    assert rel_e < 1e-5
+    check_stats(st, ref)
+
+
+def test_conv_transposed_and_concat_fp16f8(cuda):
+    x = rnd(2, 128, 32, 32, seed=5)
+    wt = rnd(128, 64, 3, 3, seed=6, scale=0.05)
+    ref = F.conv_transpose2d(x, wt, stride=2, padding=1, output_padding=1)
+    got, _ = run_conv(cuda, x, wt, stride=2, pad=1, transposed=True, split=2, stats=False)
+    assert report("convT 128->64 /fp16f8", got, ref) < 3e-4
+    emu = emulate_f8(x, wt, lambda a, b: F.conv_transpose2d(a, b, stride=2, padding=1, output_padding=1))
+    assert report("convT 128->64 /fp16f8 vs emulation", got, emu) < 1e-5
+    a, b = rnd(1, 64, 64, 64, seed=7), rnd(1, 64, 64, 64, seed=8)
+    w2 = rnd(64, 128, 3, 3, seed=9, scale=0.05)
+    ref = F.conv2d(torch.cat([a, b], dim=1), w2, padding=1)
+    got, st = run_conv(cuda, a, w2, split=2, x1=b)
+    assert report("concat 64+64->64 /fp16f8", got, ref) < 3e-4
+    check_stats(st, ref)

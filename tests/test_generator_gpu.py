@@ -97,3 +97,25 @@ def test_swap_matches_oracle(cuda, net):
     d1, d2 = (img.cpu() - img_o).abs().max().item(), (mask.cpu() - mask_o).abs().max().item()
     print("swap vs oracle: %.3e %.3e" % (d1, d2))
     assert d1 < TOL and d2 < TOL
+
+
+def test_fp16f8_mode_meets_the_parity_bar(cuda, net, monkeypatch):
+    """LWB_PRECISION=fp16f8: main product in fp16, both small products in e4m3 (2 instead of 3 MMA passes).
+    Same 1e-3 bar against the reference golden, on inference (config 2/3 path) and the full forward (config 1)."""
+    n, sd = net
+    monkeypatch.setenv("LWB_PRECISION", "fp16f8")
+    g = np.load(os.path.join(GOLD, "generator.npz"))
+    inp = S.synthetic_generator_inputs(2, 256, seed=21)
+    enc, res = n.encode_src(inp["src"].to(cuda))
+    img, mask = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda))
+    d = {"tsf_img": np.abs(sl(img) - g["inf_tsf_img"]).max(), "tsf_mask": np.abs(sl(mask) - g["inf_tsf_mask"]).max(),
+         "enc3": np.abs(enc[3][:, ::16, ::4, ::4].cpu().numpy() - g["inf_enc3"]).max(),
+         "res5": np.abs(res[5][:, ::16, ::4, ::4].cpu().numpy() - g["inf_res5"]).max()}
+    print("fp16f8 vs reference golden (inference): %s" % d)
+    assert d["tsf_img"] < TOL and d["tsf_mask"] < TOL and d["enc3"] < TOL and d["res5"] < 5 * TOL
+    inp = S.synthetic_generator_inputs(1, 256, seed=11)
+    outs = n(inp["bg"].to(cuda), inp["src"].to(cuda), inp["tsf"].to(cuda), inp["T"].to(cuda))
+    for name, t in zip(("img_bg", "src_img", "src_mask", "tsf_img", "tsf_mask"), outs):
+        dd = np.abs(sl(t) - g["fwd_" + name]).max()
+        print("fp16f8 forward %-9s vs reference golden: %.3e" % (name, dd))
+        assert dd < TOL

@@ -44,18 +44,22 @@ def test_stock_torch_and_reference_kernels_vs_this_library(cuda):
     out = {"batch": B, "image_size": size}
 
     # --- generator.inference: stock ATen/cuDNN (the reference modules' ops) -------------------------------
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     enc_o, res_o = G.encode_src(src, sd_gpu)
     enc_b = [e.expand(B, -1, -1, -1).contiguous() for e in enc_o]          # reference grid_sample needs equal N
     res_b = [r.expand(B, -1, -1, -1).contiguous() for r in res_o]
-    for tf32 in (False, True):
-        torch.backends.cudnn.allow_tf32 = tf32
-        torch.backends.cuda.matmul.allow_tf32 = tf32
-        torch.backends.cudnn.benchmark = True
-        ms = timeit(lambda: G.inference(enc_b, res_b, tsf, T, sd_gpu))
-        out["stock_generator_ms_%s" % ("tf32" if tf32 else "fp32")] = ms
-    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False                     # strict fp32 first: this run is also the parity reference
     torch.backends.cuda.matmul.allow_tf32 = False
     ref_img, ref_mask = G.inference(enc_b, res_b, tsf, T, sd_gpu)
+    out["stock_generator_ms_fp32"] = timeit(lambda: G.inference(enc_b, res_b, tsf, T, sd_gpu))
+    torch.backends.cudnn.allow_tf32 = True                      # torch's default on Ampere+
+    torch.backends.cuda.matmul.allow_tf32 = True
+    tf_img, _ = G.inference(enc_b, res_b, tsf, T, sd_gpu)
+    out["stock_generator_ms_tf32"] = timeit(lambda: G.inference(enc_b, res_b, tsf, T, sd_gpu))
+    out["stock_tf32_vs_stock_fp32_max_abs"] = (tf_img - ref_img).abs().max().item()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
     enc, res = n.encode_src(src)
     out["lwb_generator_ms_fp16x3"] = timeit(lambda: n.inference(enc, res, tsf, T))

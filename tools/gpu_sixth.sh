@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
 grep -h "vs reference golden\|vs oracle\|max-abs" gpurun_out/pytest_gpu.log | head -20
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench1.log 2>&1; echo "bench1 rc=$?"
 python - <<PY
