@@ -20,7 +20,7 @@ fallback: without the CUDA library the calls raise.
 
 Extensions over the reference (all optional): source features may have batch 1 while the target
 batch is B (torch's grid_sample cannot broadcast); ``LWB_PRECISION=fp16`` selects the
-single-pass "fast" mode (default ``fp16x3`` meets the 1e-3 parity bar); ``LWB_ALIGN_CORNERS=1``
+single-pass "fast" mode (the default ``fp16f8`` and ``fp16x3`` both meet the 1e-3 parity bar, see _split_mode); ``LWB_ALIGN_CORNERS=1``
 selects torch-1.2 grid_sample semantics (default 0 = installed-torch semantics = the oracle).
 """
 import os
@@ -32,12 +32,19 @@ from . import kernels as K
 from ._lib import LwbError
 
 
+DEFAULT_PRECISION = "fp16f8"
+
+
+def precision_mode():
+    return os.environ.get("LWB_PRECISION", DEFAULT_PRECISION)
+
+
 def _split_mode():
     """LWB_PRECISION -> operand split code of the conv engine (lwb_conv_desc.split):
     fp16x3 = 1: x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, all fp16 (3 MMAs per K step);
     fp16f8 = 2: x_hi*w_hi in fp16 + (x*w_lo, x_lo*w) in e4m3 at twice the rate (2 MMA-equivalents per K step);
     fp16   = 0: single pass (not parity-gated)."""
-    mode = os.environ.get("LWB_PRECISION", "fp16x3")
+    mode = precision_mode()
     codes = {"fp16": 0, "fp16x3": 1, "fp16f8": 2}
     if mode not in codes:
         raise LwbError("LWB_PRECISION must be fp16x3, fp16f8 or fp16")
@@ -53,7 +60,7 @@ def _halo_mode():
     kernel for the row-K stem and the skippers + 7x7 heads on tensor cores; 'all' = also the residual blocks.
     The halo variant is correct (tests/test_conv_gpu.py) but measured 10-30% SLOWER than per-tap loads on B200
     and the N=16 tensor-core heads 3x slower than the CUDA-core kernel, hence the default."""
-    if os.environ.get("LWB_PRECISION", "fp16x3") == "fp16f8":
+    if precision_mode() == "fp16f8":
         return '0'                                         # the halo kernel has no fp8 path
     return os.environ.get("LWB_HALO", "0")
 

@@ -1,7 +1,7 @@
 """End-to-end GPU parity of the generator mirror (tcgen05 conv engine + fused LWB) against
   * the slices the REFERENCE modules produced (tests/golden/generator.npz), and
   * the full outputs of the functional restatement (oracle/generator_ref.py) on CPU.
-Bar (BASELINE.json north_star): 1e-3 max-abs on fp32 pixels in the default fp16x3 mode."""
+Bar (BASELINE.json north_star): 1e-3 max-abs on fp32 pixels, met by the default fp16f8 mode and by fp16x3."""
 import os
 
 import numpy as np
@@ -99,11 +99,13 @@ def test_swap_matches_oracle(cuda, net):
     assert d1 < TOL and d2 < TOL
 
 
-def test_fp16f8_mode_meets_the_parity_bar(cuda, net, monkeypatch):
-    """LWB_PRECISION=fp16f8: main product in fp16, both small products in e4m3 (2 instead of 3 MMA passes).
-    Same 1e-3 bar against the reference golden, on inference (config 2/3 path) and the full forward (config 1)."""
+@pytest.mark.parametrize("mode", ["fp16f8", "fp16x3"])
+def test_both_parity_modes_meet_the_bar(cuda, net, monkeypatch, mode):
+    """fp16f8 (default): main product in fp16, both small products in e4m3 (2 instead of 3 MMA passes);
+    fp16x3: all three products in fp16.  Same 1e-3 bar against the reference golden, on inference
+    (config 2/3 path) and the full forward (config 1)."""
     n, sd = net
-    monkeypatch.setenv("LWB_PRECISION", "fp16f8")
+    monkeypatch.setenv("LWB_PRECISION", mode)
     g = np.load(os.path.join(GOLD, "generator.npz"))
     inp = S.synthetic_generator_inputs(2, 256, seed=21)
     enc, res = n.encode_src(inp["src"].to(cuda))
@@ -111,11 +113,11 @@ def test_fp16f8_mode_meets_the_parity_bar(cuda, net, monkeypatch):
     d = {"tsf_img": np.abs(sl(img) - g["inf_tsf_img"]).max(), "tsf_mask": np.abs(sl(mask) - g["inf_tsf_mask"]).max(),
          "enc3": np.abs(enc[3][:, ::16, ::4, ::4].cpu().numpy() - g["inf_enc3"]).max(),
          "res5": np.abs(res[5][:, ::16, ::4, ::4].cpu().numpy() - g["inf_res5"]).max()}
-    print("fp16f8 vs reference golden (inference): %s" % d)
+    print("%s vs reference golden (inference): %s" % (mode, d))
     assert d["tsf_img"] < TOL and d["tsf_mask"] < TOL and d["enc3"] < TOL and d["res5"] < 5 * TOL
     inp = S.synthetic_generator_inputs(1, 256, seed=11)
     outs = n(inp["bg"].to(cuda), inp["src"].to(cuda), inp["tsf"].to(cuda), inp["T"].to(cuda))
     for name, t in zip(("img_bg", "src_img", "src_mask", "tsf_img", "tsf_mask"), outs):
         dd = np.abs(sl(t) - g["fwd_" + name]).max()
-        print("fp16f8 forward %-9s vs reference golden: %.3e" % (name, dd))
+        print("%s forward %-9s vs reference golden: %.3e" % (mode, name, dd))
         assert dd < TOL
