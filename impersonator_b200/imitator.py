@@ -263,6 +263,23 @@ class Imitator(object):
                 outputs.append(preds[0].permute(1, 2, 0).cpu().numpy())
                 self._maybe_save(outputs[-1], tgt_paths[t], output_dir, t)
             return outputs
+        # Chunks are pipelined: the D2H of chunk i runs on a copy stream while chunk i+1 computes; the host only
+        # waits for a chunk's copy when it has already queued the next chunk (and once at the end).
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        pending = []
+
+        def drain(keep):
+            while len(pending) > keep:
+                a0, b0, h_f, h_u8, done = pending.pop(0)
+                done.synchronize()
+                host = h_u8 if as_uint8 else h_f
+                for j in range(b0 - a0):
+                    outputs.append(host[j])
+                    if output_dir:
+                        self._maybe_save(h_u8[j], tgt_paths[a0 + j], output_dir, a0 + j, is_bgr_u8=True)
+
         for (a, b) in self._chunks(length):
             smpls = torch.as_tensor(np.stack([np.asarray(s, dtype=np.float32) for s in tgt_smpls[a:b]]))
             tsf_inputs = self.transfer_params_by_smpl(smpls, cam_strategy, t=a)
@@ -270,12 +287,20 @@ class Imitator(object):
             preds = self.forward(tsf_inputs, self.tsf_info['T'], host_layout=dict(hwc=not as_uint8, u8=want_u8))
             if visualizer is not None:
                 visualizer.vis_named_img('pred_' + cam_strategy, preds)
-            host_u8 = self._to_host(self._out_u8, sync=as_uint8) if want_u8 else None
-            host = host_u8 if as_uint8 else self._to_host(self._out_hwc)        # one sync per chunk
-            for j in range(b - a):
-                outputs.append(host[j])
-                if output_dir:
-                    self._maybe_save(host_u8[j], tgt_paths[a + j], output_dir, a + j, is_bgr_u8=True)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(ready)
+                h_f = self._to_host(self._out_hwc, sync=False) if not as_uint8 else None
+                h_u8 = self._to_host(self._out_u8, sync=False) if want_u8 else None
+                for t in (self._out_hwc, self._out_u8):
+                    if t is not None:
+                        t.record_stream(self._copy_stream)
+                done = torch.cuda.Event()
+                done.record(self._copy_stream)
+            pending.append((a, b, h_f, h_u8, done))
+            drain(keep=1)
+        drain(keep=0)
         self._last_frame_info()
         return outputs
 
@@ -286,7 +311,7 @@ class Imitator(object):
 
     @staticmethod
     def _to_host(t, sync=True):
-        """Device -> pinned host (torch's caching host allocator), one async copy (+ one sync)."""
+        """Device -> pinned host (torch's caching host allocator), one async copy on the current stream (+ one sync)."""
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t, non_blocking=True)
         if sync:
