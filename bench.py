@@ -374,8 +374,15 @@ def main():
         conv = prof["conv"]
         issue_units = {"fp16x3": 3.0, "fp16f8": 2.0, "fp16": 1.0}[mode]
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))["bytes_per_launch"]
+        except Exception:
+            pass
         line["roofline"] = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM, all conv layers of generator.inference)",
-                            "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+                            "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
+                            "traffic_note": "mean DRAM bytes per conv launch from the committed ncu pass (profiles/conv_traffic.json), "
+                                            "not re-measured in this run",
                             "peak_source": "bf16_tflops_sustained, " + src,
                             "algorithmic_gflop_per_step": conv["flops"] / prof["passes"] / 1e9,
                             "issued_mma_gflop_per_step": 3 * conv["flops"] / prof["passes"] / 1e9,

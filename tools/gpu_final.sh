@@ -2,6 +2,7 @@
 # Round-end evidence: full GPU suite, smoke, bench (both arms), steady-state launch list, targeted ncu captures -> CSV.
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+LWB_RUN_STOCK=1 timeout 900 python -m pytest tests/test_stock_gpu_compare.py -m gpu -q -s -p no:cacheprovider --timeout 800 > gpurun_out/stock.log 2>&1; echo "stock rc=$?"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
 timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>gpurun_out/bench_ref.err; echo "bench ref rc=$?"
 timeout 900 python bench.py --steps 30 --warmup 5 > gpurun_out/bench.json 2>gpurun_out/bench.err; echo "bench rc=$?"
@@ -12,7 +13,10 @@ cap() {  # name, kernel regex, skip, count
   timeout 900 $NCU --set full --import-source on -k regex:"$2" -s $3 -c $4 -o gpurun_out/$1 -f $BENCH > gpurun_out/$1.log 2>&1
   echo "$1 rc=$?"
   ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1.raw.csv 2>/dev/null
+  rm -f gpurun_out/$1.ncu-rep
 }
+# DRAM traffic of every conv launch of one step (roofline.traffic): cheap metrics pass
+timeout 600 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:k_conv_tc -c 64 --csv --log-file gpurun_out/conv_traffic.csv $BENCH > gpurun_out/ncu_traffic.log 2>&1; echo "traffic rc=$?"
 cap conv_res "k_conv_tc" 6 2
 cap conv_skip256 "k_conv_tc" 30 1
 cap norm "k_norm_act" 0 2
