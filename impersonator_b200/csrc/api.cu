@@ -1,5 +1,6 @@
 // Error plumbing and device queries of the lwb_b200 C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -28,6 +29,13 @@ int sm_count()
             return 148;
     }
     return cached;
+}
+
+bool pdl_enabled()
+{
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("LWB_PDL"); cached = (e && atoi(e) == 0) ? 0 : 1; }
+    return cached != 0;
 }
 
 }  // namespace lwb

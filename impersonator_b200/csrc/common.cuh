@@ -28,6 +28,25 @@ static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();
 
+// Programmatic dependent launch (LWB_PDL, default on): kernels launched through launch_pdl may be scheduled while the
+// previous kernel of the stream drains; each of them executes pdl_wait() before its first global-memory access and
+// pdl_trigger() to let its own successor do the same.  Both are no-ops for a kernel launched the plain way.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): the 2-term operand split of the conv engine.
 __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);

@@ -358,6 +358,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constan
     if (CL > 1) cluster_sync_all();              // peers' barriers are initialised before any multicast can land
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    lwb::pdl_wait();                             // see k_conv_tc2: global memory only after the preceding kernel completed
+    lwb::pdl_trigger();
 
     const int nchunks = P.chunks0 + P.chunks1;
     const int ksteps = P.ntaps * nchunks;
@@ -551,6 +553,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2(const __grid_consta
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above touched only this CTA's shared memory / TMEM; global memory (operands, output, statistics) is
+    // produced / still read by the preceding kernel of the stream: wait for it (no-op without a programmatic launch)
+    lwb::pdl_wait();
+    lwb::pdl_trigger();                                  // the statistics-finalize kernel may be scheduled early (it waits too)
 
     const int nchunks = P.chunks0 + P.chunks1;
     const int ksteps = P.ntaps * nchunks;
@@ -941,7 +947,7 @@ int launch_cl(const Launch& L, cudaStream_t st)
     { static int forced = -1; if (forced < 0) { const char* e = getenv("LWB_STAGES"); forced = e ? atoi(e) : 0; }
       pp.stages = (forced >= 2 && forced < C::STAGES) ? forced : C::STAGES; }
     if (CL == 1) {
-        k_conv_tc<N_TILE, SPLIT, CL, KC><<<L.grid, NUM_THREADS, C::SMEM_BYTES, st>>>(L.p);
+        LWB_CUDA_OK(lwb::launch_pdl(k_conv_tc<N_TILE, SPLIT, CL, KC>, dim3(L.grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, L.p));
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
@@ -966,10 +972,15 @@ int launch_2sm(const Launch& L, cudaStream_t st)
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    // Programmatic dependent launch (LWB_PDL=1): the CTAs may be scheduled while the previous kernel of the stream
+    // drains; they set up barriers / TMEM and then block in griddepcontrol.wait until that kernel has completed.
+    const int pdl = lwb::pdl_enabled() ? 1 : 0;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
     LWB_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tc2<N_TILE, SPLIT>, L.p));
     LWB_LAUNCH_OK();
     return LWB_OK;

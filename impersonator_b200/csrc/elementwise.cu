@@ -148,6 +148,8 @@ __global__ void k_finalize_stats(const double* __restrict__ stats, const float* 
                                  const float* __restrict__ beta, float eps, int n, int c, double inv_hw,
                                  float2* __restrict__ ss)
 {
+    lwb::pdl_wait();                                     // the statistics come from the conv kernel just before
+    lwb::pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * c) return;
     const int ch = i % c;
@@ -206,6 +208,8 @@ template <bool WARP>
 __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
 {
     constexpr int R = 2;                                 // pixel rounds per thread
+    lwb::pdl_wait();                                     // raw / scale-shift / residual come from the kernels before
+    lwb::pdl_trigger();                                  // the next conv may set up while this grid drains
     const int groups = P.c >> 3;
     const int ppb = 256 / groups;                        // pixels per block per round (groups <= 256)
     const int g = threadIdx.x % groups, lp = threadIdx.x / groups;
@@ -490,9 +494,8 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
     LWB_CHECK_ARG(!warp_src || (T && th > 0 && tw > 0 && (src_batch == 1 || src_batch == n)), "bad warp arguments");
     cudaStream_t st = (cudaStream_t)stream;
     if (stats) {
-        k_finalize_stats<<<lwb::ceil_div((long)n * c, 256), 256, 0, st>>>(
-            stats, gamma, beta, eps, n, c, 1.0 / ((double)h * w), (float2*)scale_shift_ws);
-        LWB_LAUNCH_OK();
+        LWB_CUDA_OK(lwb::launch_pdl(k_finalize_stats, dim3(lwb::ceil_div((long)n * c, 256)), dim3(256), 0, st,
+                                    stats, gamma, beta, eps, n, c, 1.0 / ((double)h * w), (float2*)scale_shift_ws));
     }
     NormActParams P;
     P.raw = raw; P.ss = stats ? (const float2*)scale_shift_ws : nullptr; P.relu = relu;
@@ -503,9 +506,8 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
     const int groups = c / 8;
     LWB_CHECK_ARG(groups <= 256 && 256 % groups == 0, "channels / 8 must divide 256");
     const long blocks = lwb::ceil_div((long)n * h * w, (256 / groups) * 2);
-    if (warp_src) k_norm_act<true><<<(unsigned)blocks, 256, 0, st>>>(P);
-    else          k_norm_act<false><<<(unsigned)blocks, 256, 0, st>>>(P);
-    LWB_LAUNCH_OK();
+    if (warp_src) LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<true>, dim3((unsigned)blocks), dim3(256), 0, st, P));
+    else          LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<false>, dim3((unsigned)blocks), dim3(256), 0, st, P));
     return LWB_OK;
 }
 
