@@ -68,3 +68,27 @@ def test_synthetic_smpl_model_has_the_pickle_layout():
     assert dd['f'].shape == (13776, 3)
     th = S.synthetic_smpl_params(3, seed=1)
     assert th.shape == (3, 85) and th.dtype == torch.float32
+
+
+def test_oracle_self_correspondence_is_the_identity_warp():
+    """Domain round trip (size independent): a frame corresponded with ITSELF must give T = pixel-centre coordinates on
+    every covered pixel (cal_bc_transform, utils/nmr.py:617-659, inverts the rasterizer's barycentrics) and therefore
+    warp the source image onto itself; uncovered pixels keep -2.  Pins the oracle's conventions (y flip, row flip,
+    align_corners=False sampling) without any golden file."""
+    from oracle import nmr_ref
+    size = 128
+    v, f = S.uv_sphere()
+    cam, verts = S.synthetic_frames(1, seed=8, base_verts=v)
+    tabs = S.synthetic_tables()
+    ys, xs = torch.meshgrid(torch.arange(size, dtype=torch.float32), torch.arange(size, dtype=torch.float32), indexing="ij")
+    gx, gy = (2 * xs + 1 - size) / size, (2 * ys + 1 - size) / size
+    src = torch.stack([torch.sin(3 * gx) * torch.cos(2 * gy), gx * gy, torch.cos(4 * gx + gy)])[None]
+    f2v, fim, _ = nmr_ref.render_fim_wim(cam, verts, f, size)
+    out = nmr_ref.correspond(cam, verts, f, tabs["map_fn"], nmr_ref.src_p2verts(f2v), src, size)
+    cov = fim[0] >= 0
+    assert 0.05 < cov.float().mean() < 0.6
+    T = out["T"][0]
+    assert (T[..., 0] - gx)[cov].abs().max() < 5e-4 and (T[..., 1] - gy)[cov].abs().max() < 5e-4
+    assert torch.all(T[~cov] == -2)
+    assert (out["tsf_img"][0] - src[0])[:, cov].abs().max() < 2e-3
+    assert torch.all(out["tsf_img"][0][:, ~cov] == 0)

@@ -162,3 +162,28 @@ def test_correspond_source_pass_matches_render_fim_wim(cuda):
     ys, xs = torch.meshgrid(torch.arange(256), torch.arange(256), indexing="ij")
     gx = (2.0 * xs + 1 - 256) / 256
     assert (T[0][cov][:, 0] - gx[cov]).abs().max().item() < 2e-2
+
+
+def test_self_correspondence_is_the_identity_warp(cuda):
+    """Round trip through lwb_correspond at the full 256^2 / 512^2 sizes: frame 0 corresponded with itself gives
+    T = pixel centres and tsf_img = src_img on covered pixels, -2 / 0 elsewhere (no oracle involved)."""
+    v, f = S.uv_sphere()
+    tabs = S.synthetic_tables()
+    for size in (256, 512):
+        cam, verts = S.synthetic_frames(2, seed=8, base_verts=v)
+        ys, xs = torch.meshgrid(torch.arange(size, dtype=torch.float32), torch.arange(size, dtype=torch.float32), indexing="ij")
+        gx, gy = (2 * xs + 1 - size) / size, (2 * ys + 1 - size) / size
+        src = torch.stack([torch.sin(3 * gx) * torch.cos(2 * gy), gx * gy, torch.cos(4 * gx + gy)])[None]
+        from impersonator_b200.nmr import SMPLRenderer
+        r = SMPLRenderer(image_size=size, faces=f.numpy(), map_fn=tabs["map_fn"]).to(cuda)
+        src_pass = r.correspond(cam[:1].to(cuda), verts[:1].to(cuda), None, None, want_f2verts=True)     # personalize side
+        p2v = src_pass["f2verts"][:, :, :, 0:2].clone()
+        p2v[:, :, :, 1] *= -1                                                  # models/imitator.py:105-107
+        out = r.correspond(cam.to(cuda), verts.to(cuda), p2v.contiguous(), src.to(cuda))
+        torch.cuda.synchronize()
+        fim, T, img = out["fim"][0].cpu(), out["T"][0].cpu(), out["tsf_img"][0].cpu()
+        cov = fim >= 0
+        assert 0.05 < cov.float().mean() < 0.6
+        assert (T[..., 0] - gx)[cov].abs().max() < 5e-4 and (T[..., 1] - gy)[cov].abs().max() < 5e-4
+        assert torch.all(T[~cov] == -2) and torch.all(img[:, ~cov] == 0)
+        assert (img - src[0])[:, cov].abs().max() < 2e-3
