@@ -287,3 +287,19 @@ def test_conv_transposed_and_concat_fp16f8(cuda):
     got, st = run_conv(cuda, a, w2, split=2, x1=b)
     assert report("concat 64+64->64 /fp16f8", got, ref) < 3e-4
     check_stats(st, ref)
+
+
+@pytest.mark.parametrize("split", [1, 2])
+def test_conv_is_exactly_homogeneous_at_full_batch(cuda, split):
+    """Size-independent property at the BASELINE batch (16 x 512 x 32 x 32, the residual-block layer): scaling the input
+    by a power of two scales every operand of the hi/lo (and e4m3) split exactly, so the output must scale bit-exactly;
+    the same tile schedule must also give the same bits for every image of a batch of identical images."""
+    x1 = rnd(1, 512, 32, 32, seed=3)
+    x = x1.expand(16, -1, -1, -1).contiguous()
+    wt = rnd(512, 512, 3, 3, seed=4, scale=0.02)
+    y, _ = run_conv(cuda, x, wt, split=split, stats=False)
+    y2, _ = run_conv(cuda, 2 * x, wt, split=split, stats=False)
+    assert torch.equal(y2, 2 * y)
+    assert torch.equal(y[0], y[15]) and torch.equal(y[0], y[7])
+    ref = F.conv2d(x1, wt, padding=1)
+    assert report("512->512 @32 batch 16 (image 0)", y[:1], ref) < (2e-4 if split == 1 else 3e-4)
