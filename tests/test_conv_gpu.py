@@ -290,16 +290,16 @@ def test_conv_transposed_and_concat_fp16f8(cuda):
 
 
 @pytest.mark.parametrize("split", [1, 2])
-def test_conv_is_exactly_homogeneous_at_full_batch(cuda, split):
-    """Size-independent property at the BASELINE batch (16 x 512 x 32 x 32, the residual-block layer): scaling the input
-    by a power of two scales every operand of the hi/lo (and e4m3) split exactly, so the output must scale bit-exactly;
-    the same tile schedule must also give the same bits for every image of a batch of identical images."""
+def test_conv_homogeneity_and_batch_invariance_at_full_batch(cuda, split):
+    """Size-independent properties at the BASELINE batch (16 x 512 x 32 x 32, the residual-block layer): conv(2x) = 2 conv(x)
+    up to the fp16-subnormal rounding of the lo operands (|lo| < 6e-5 loses bits, so not bit-exact), and every image of a
+    batch of identical images gets the same bits (same tile schedule, same accumulation order)."""
     x1 = rnd(1, 512, 32, 32, seed=3)
     x = x1.expand(16, -1, -1, -1).contiguous()
     wt = rnd(512, 512, 3, 3, seed=4, scale=0.02)
     y, _ = run_conv(cuda, x, wt, split=split, stats=False)
     y2, _ = run_conv(cuda, 2 * x, wt, split=split, stats=False)
-    assert torch.equal(y2, 2 * y)
+    assert report("conv(2x) vs 2 conv(x)", y2, 2 * y) < 2e-5
     assert torch.equal(y[0], y[15]) and torch.equal(y[0], y[7])
     ref = F.conv2d(x1, wt, padding=1)
     assert report("512->512 @32 batch 16 (image 0)", y[:1], ref) < (2e-4 if split == 1 else 3e-4)
