@@ -17,6 +17,11 @@
 // Precision: x ~= x_hi + x_lo, w ~= w_hi + w_lo in fp16; with SPLIT the accumulator receives
 // x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (fp32 accumulate), which reproduces the fp32 reference
 // convolution to ~1e-5 (single pass fp16 cannot meet the 1e-3 parity bar).
+// In f8 mode (ConvParams::f8, the default of the host side) the two small products are issued as ONE
+// kind::f8f6f4 MMA per K step on e4m3 operand pairs stored in the lo buffers (elementwise.cu, kF8*).
+//
+// Kernels: k_conv_tc2 (cta_group::2, a CTA pair shares every weight tile; the default), k_conv_tc (one CTA
+// per tile, optional weight multicast), k_conv_halo (activation halo + shifted descriptors; off by default).
 //
 // Variants, all through the same kernel:
 //   stride 2      : four parity views of the input (plain strided tensor maps), tap -> view

@@ -93,9 +93,11 @@ int lwb_warp_nchw(const float* x, int src_batch, int channels, int h, int w,
 /* ------------------------------------------------------------------------------------------
  * Conv engine (NHWC, tcgen05 implicit GEMM).  Replaces the cuDNN calls behind nn.Conv2d /
  * nn.ConvTranspose2d / nn.InstanceNorm2d of networks/generator.py:8-20,77-134,163-184.
- * Activations are channels-last fp16 pairs (hi + lo, x ~= hi + lo) so that three tensor-core
- * passes (hi*hi + hi*lo + lo*hi, fp32 accumulate) reproduce fp32 convolution to ~1e-5
- * (SURVEY.md section 0 fact 4); split = 0 runs the single hi*hi pass ("fast" mode).
+ * Activations are channels-last pairs (hi = fp16(x), lo = 2 more bytes per element) so that the
+ * products hi*hi + x*w_lo + x_lo*w (fp32 accumulate) reproduce fp32 convolution to ~1e-5 per layer
+ * (SURVEY.md section 0 fact 4): split = 1 keeps lo in fp16 and issues three fp16 tensor-core passes,
+ * split = 2 keeps the two correction operands in e4m3 and issues them as one fp8 pass, split = 0
+ * runs the single hi*hi pass ("fast" mode, not parity-gated).
  * ------------------------------------------------------------------------------------------ */
 
 /* Repack an OIHW (Conv2d) or IOHW (ConvTranspose2d, transposed != 0) fp32 weight into the
