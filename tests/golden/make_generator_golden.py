@@ -4,6 +4,7 @@ Imports the reference's own networks/generator.py (pure torch.nn; ipdb/h5py stub
 deterministic weights of impersonator_b200.synthetic.fill_state_dict(seed=0) into it, runs
   ImpersonatorGenerator.forward      (networks/generator.py:204-211)   B=1   (BASELINE config 1)
   encode_src + inference             (:213-214, :277-301)              B=2
+  swap                               (:245-275)                        B=1, two sources
 on impersonator_b200.synthetic.synthetic_generator_inputs and stores strided slices of every output.
 It also checks oracle/generator_ref.py (the functional restatement) against the reference modules
 on the full tensors, so the restatement is pinned to the reference here, and the slices pin both
@@ -65,6 +66,20 @@ def main():
     out["inf_tsf_mask"] = sl(mask)
     out["inf_enc3"] = enc[3][:, ::16, ::4, ::4].contiguous().numpy()
     out["inf_res5"] = res[5][:, ::16, ::4, ::4].contiguous().numpy()
+    # swap (appearance transfer, networks/generator.py:245-275): two sources, two flows
+    a = synthetic.synthetic_generator_inputs(1, 256, seed=31)
+    b = synthetic.synthetic_generator_inputs(1, 256, seed=41)
+    e12, r12 = net.encode_src(a["src"])
+    e21, r21 = net.encode_src(b["src"])
+    s_img, s_mask = net.swap(a["tsf"], e12, e21, r12, r21, a["T"], b["T"])
+    o12, q12 = G.encode_src(a["src"], sd)
+    o21, q21 = G.encode_src(b["src"], sd)
+    m_img, m_mask = G.swap(a["tsf"], o12, o21, q12, q21, a["T"], b["T"], sd)
+    for name, x, y in (("swap_img", s_img, m_img), ("swap_mask", s_mask, m_mask)):
+        d = (x - y).abs().max().item()
+        print("swap %-9s restatement-vs-reference max-abs %.3g" % (name, d))
+        assert d < 1e-5
+        out[name] = sl(x)
     np.savez_compressed(os.path.join(HERE, "generator.npz"), **out)
     print("wrote generator.npz", {k: v.shape for k, v in out.items() if k not in ("keys", "shapes")})
 

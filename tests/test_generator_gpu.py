@@ -97,6 +97,10 @@ def test_swap_matches_oracle(cuda, net):
     d1, d2 = (img.cpu() - img_o).abs().max().item(), (mask.cpu() - mask_o).abs().max().item()
     print("swap vs oracle: %.3e %.3e" % (d1, d2))
     assert d1 < TOL and d2 < TOL
+    g = np.load(os.path.join(GOLD, "generator.npz"))            # the reference modules' own swap() on the same inputs
+    g1, g2 = np.abs(sl(img) - g["swap_img"]).max(), np.abs(sl(mask) - g["swap_mask"]).max()
+    print("swap vs reference golden: %.3e %.3e" % (g1, g2))
+    assert g1 < TOL and g2 < TOL
 
 
 @pytest.mark.parametrize("mode", ["fp16f8", "fp16x3"])
