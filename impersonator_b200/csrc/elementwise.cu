@@ -204,11 +204,10 @@ struct NormActParams {
 // computed once (by one thread) and shared through smem instead of once per channel octet.
 struct TapRec { int o00, m; float w00, w01, w10, w11; };
 
-// R = pixel rounds per thread: 2 in general; the plain variant (no residual, no warp -- 13 of the 22 calls, all the
-// large layers) has the registers for 4, i.e. 128 B of loads in flight per thread.
-template <bool WARP, int R>
+template <bool WARP>
 __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
 {
+    constexpr int R = 2;                                 // pixel rounds per thread
     lwb::pdl_wait();                                     // raw / scale-shift / residual come from the kernels before
     lwb::pdl_trigger();                                  // the next conv may set up while this grid drains
     const int groups = P.c >> 3;
@@ -250,14 +249,13 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
         const float4 a = ok[r] ? __ldg(src) : make_float4(0, 0, 0, 0), c = ok[r] ? __ldg(src + 1) : make_float4(0, 0, 0, 0);
         v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w; v[r][4] = c.x; v[r][5] = c.y; v[r][6] = c.z; v[r][7] = c.w;
     }
-    float res[R == 2 ? R : 1][8];                        // R = 4 is only launched without a residual
-    if (R == 2 && P.residual) {
+    float res[R][8];
+    if (P.residual) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const float4* src = reinterpret_cast<const float4*>(P.residual + off[r]);
             const float4 a = ok[r] ? __ldg(src) : make_float4(0, 0, 0, 0), c = ok[r] ? __ldg(src + 1) : make_float4(0, 0, 0, 0);
-            float* rr = res[R == 2 ? r : 0];
-            rr[0] = a.x; rr[1] = a.y; rr[2] = a.z; rr[3] = a.w; rr[4] = c.x; rr[5] = c.y; rr[6] = c.z; rr[7] = c.w;
+            res[r][0] = a.x; res[r][1] = a.y; res[r][2] = a.z; res[r][3] = a.w; res[r][4] = c.x; res[r][5] = c.y; res[r][6] = c.z; res[r][7] = c.w;
         }
     }
 #pragma unroll
@@ -275,9 +273,9 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
 #pragma unroll
             for (int k = 0; k < 8; k++) v[r][k] = fmaxf(v[r][k], 0.f);
         }
-        if (R == 2 && P.residual) {
+        if (P.residual) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[r][k] += res[R == 2 ? r : 0][k];
+            for (int k = 0; k < 8; k++) v[r][k] += res[r][k];
         }
         if (WARP) {
             const TapRec tp = s_tap[r * ppb + lp];
@@ -507,13 +505,9 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
     P.y_f32 = y_f32; P.y_hi = (__half*)y_hi; P.y_lo = (__half*)y_lo; P.lo_format = lo_format;
     const int groups = c / 8;
     LWB_CHECK_ARG(groups <= 256 && 256 % groups == 0, "channels / 8 must divide 256");
-    static int r4 = -1;
-    if (r4 < 0) { const char* e = getenv("LWB_NORM_R4"); r4 = (e && atoi(e) != 0) ? 1 : 0; }
-    const bool plain4 = r4 && !warp_src && !residual && (long)n * h * w >= 4096;
-    const long blocks = lwb::ceil_div((long)n * h * w, (256 / groups) * (plain4 ? 4 : 2));
-    if (warp_src)    LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<true, 2>, dim3((unsigned)blocks), dim3(256), 0, st, P));
-    else if (plain4) LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<false, 4>, dim3((unsigned)blocks), dim3(256), 0, st, P));
-    else             LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<false, 2>, dim3((unsigned)blocks), dim3(256), 0, st, P));
+    const long blocks = lwb::ceil_div((long)n * h * w, (256 / groups) * 2);
+    if (warp_src) LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<true>, dim3((unsigned)blocks), dim3(256), 0, st, P));
+    else          LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<false>, dim3((unsigned)blocks), dim3(256), 0, st, P));
     return LWB_OK;
 }
 
