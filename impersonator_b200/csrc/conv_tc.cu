@@ -64,7 +64,7 @@ struct ConvParams {
     double* stats;
     int stages;                       // pipeline depth actually used (<= Cfg::STAGES; LWB_STAGES, diagnostic)
     int f8;                           // SPLIT stages hold [A_hi | A_lo8 | B_hi | B_lo8]: 1 f16 + 1 f8f6f4 MMA per K step
-    float out_scale;                  // accumulator -> output (2^-15 in f8 mode, else 1)
+    float out_scale;                  // accumulator -> output (2^-w_exp in f8 mode, else 1)
 };
 
 template <int N_TILE, bool SPLIT, int KC = KCHUNK>
@@ -1017,6 +1017,7 @@ int launch(const Launch& L, cudaStream_t st)
     }
     switch (L.n_tile) {
         case 16:  return L.split ? launch_one<16, true>(L, st) : launch_one<16, false>(L, st);
+        case 32:  return L.split ? launch_one<32, true>(L, st) : launch_one<32, false>(L, st);
         case 64:  return L.split ? launch_one<64, true>(L, st) : launch_one<64, false>(L, st);
         case 128: return L.split ? launch_one<128, true>(L, st) : launch_one<128, false>(L, st);
         case 256: return L.split ? launch_one<256, true>(L, st) : launch_one<256, false>(L, st);
@@ -1031,6 +1032,7 @@ int pick_n_tile(int cout, bool split, int forced)
     if (cout % 256 == 0) return 256;      // measured on B200: split N=256 (2 stages) 473 TF/s vs N=128 (3 stages) 420
     if (cout % 128 == 0) return 128;
     if (cout % 64 == 0) return 64;
+    if (cout % 32 == 0) return 32;
     if (cout % 16 == 0) return 16;
     return -1;
 }
@@ -1073,6 +1075,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     LWB_CHECK_ARG(!f8 || (!d->rowk && !d->halo), "the fp8 lo mode is not available for row-K / halo plans");
     LWB_CHECK_ARG(d->n > 0 && d->h_in > 0 && d->w_in > 0 && d->cout > 0, "non-positive size");
     LWB_CHECK_ARG(d->cout % 16 == 0, "cout must be a multiple of 16");
+    LWB_CHECK_ARG(!f8 || (d->w_exp >= -40 && d->w_exp <= 60), "w_exp out of range");
     int n_tile = pick_n_tile(d->cout, split, d->n_tile);
     if (d->halo && split && n_tile == 256 && d->n_tile == 0) n_tile = 128;      // halo + split: the 256-wide weight ring does not fit
     LWB_CHECK_ARG(n_tile > 0 && d->cout % n_tile == 0, "no N tile divides cout");
@@ -1116,7 +1119,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.out = getenv("LWB_DEBUG_NOSTORE") ? nullptr : out_raw; p.out_h = d->h_out; p.out_w = d->w_out; p.cout = d->cout;
         p.stats = stats;
         p.f8 = f8 ? 1 : 0;
-        p.out_scale = f8 ? (1.f / 32768.f) : 1.f;      // weights are packed x 2^15 in f8 mode (lwb_pack_conv_weight_f8)
+        p.out_scale = f8 ? ldexpf(1.f, -d->w_exp) : 1.f;      // weights are packed x 2^w_exp in f8 mode (lwb_pack_conv_weight_f8)
         L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl; L.kc = d->rowk ? KCHUNK : kc;
         L.two_sm = two_sm;
         p.stages = 64;      // clamped to Cfg::STAGES at launch
@@ -1287,7 +1290,8 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
     int t = 0;
     for (int ky = 0; ky < d->kh; ky++) for (int kx = 0; kx < d->kw; kx++) {
-        const int oy = ky * d->dil - d->pad, ox = kx * d->dil - d->pad;       // input offset relative to stride*y
+        const int oy = ky * d->dil - d->pad, ox = kx * d->dil - (d->pad_w >= 0 ? d->pad_w : d->pad);   // input offset relative to stride*y
+        if (oy < -127 || oy > 127 || ox < -127 || ox > 127) { lwb::set_error("conv_tc: tap offset out of range"); return fail(LWB_E_UNSUPPORTED); }
         if (d->stride == 1) {
             L.p.dy[t] = (signed char)oy; L.p.dx[t] = (signed char)ox; L.p.tmap[t] = 0;
         } else {

@@ -38,19 +38,24 @@ __global__ void k_pack_weight(const float* __restrict__ w, int cout, int cin, in
 
 // fp8 scales of the "fp16 + fp8" operand split (conv_tc.cu, f8 mode).  With hi = fp16(v), lo = v - hi:
 //     x * w ~= x_hi * w_hi + x * w_lo + x_lo * w            (the two small products only need ~4 bits)
-// and everything is accumulated 2^15 too large so that no fp8 operand underflows:
-//     A_hi = x_hi                 B_hi  = fp16(w_hi * 2^15)
-//     A_lo8[0:64]  = e4m3(x)      B_lo8[0:64]  = e4m3(w_lo * 2^15)
-//     A_lo8[64:128] = e4m3(x_lo * 2^12)   B_lo8[64:128] = e4m3(w * 2^3)
-// per 64-channel block (one 128 B K row); the epilogue multiplies by 2^-15.
-constexpr float kF8WScale = 32768.f, kF8XLoScale = 4096.f, kF8WHiScale = 8.f;
+// and everything is accumulated 2^E too large so that no fp8 operand underflows; E is chosen PER LAYER so that
+// max|w| * 2^E lies in [2^14, 2^15) (lwb_conv_desc.w_exp; any weight magnitude packs without overflow):
+//     A_hi = x_hi                           B_hi  = fp16(w_hi * 2^E)          (exact: a power of two)
+//     A_lo8[0:64]   = e4m3(x * 2^-4)        B_lo8[0:64]   = e4m3(w_lo * 2^(E+4))     |.| <= 2^8
+//     A_lo8[64:128] = e4m3(x_lo * 2^10)     B_lo8[64:128] = e4m3(w * 2^(E-10))       |.| <  2^5
+// per 64-channel block (one 128 B K row); the epilogue multiplies by 2^-E.  Activation range: e4m3 saturates at 448,
+// i.e. x_lo (<= half an fp16 ulp of x) clips for |x| >= 1024 and x itself for |x| >= 7168 -- the split then degrades
+// gracefully towards single-pass fp16 for those elements; k_norm_act reports it through its range flag
+// (bit 0: |y| >= 1024, bit 1: |y| >= 60000 or non-finite = the fp16 hi operand itself overflows).
+constexpr float kF8XScale = 1.f / 16.f, kF8XLoScale = 1024.f;
+constexpr float kF8WLoRel = 16.f, kF8WRel = 1.f / 1024.f;       // relative to the layer's 2^E
 
 __device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
 
-// weights, f8 mode: hi [tap][cout_pad][cin_pad] fp16 = w_hi * 2^15;  lo8: the same 2 bytes per element, per 64-channel
-// block [64 x e4m3(w_lo * 2^15)][64 x e4m3(w * 2^3)]
+// weights, f8 mode: hi [tap][cout_pad][cin_pad] fp16 = w_hi * 2^E;  lo8: the same 2 bytes per element, per 64-channel
+// block [64 x e4m3(w_lo * 2^(E+4))][64 x e4m3(w * 2^(E-10))]
 __global__ void k_pack_weight_f8(const float* __restrict__ w, int cout, int cin, int kh, int kw, int transposed,
-                                 int cout_pad, int cin_pad, __half* __restrict__ hi, uint8_t* __restrict__ lo8)
+                                 int cout_pad, int cin_pad, float wscale, __half* __restrict__ hi, uint8_t* __restrict__ lo8)
 {
     const long total = (long)kh * kw * cout_pad * cin_pad;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -65,10 +70,10 @@ __global__ void k_pack_weight_f8(const float* __restrict__ w, int cout, int cin,
         }
         const __half h = __float2half_rn(v);
         const float lo = v - __half2float(h);
-        hi[i] = __float2half_rn(__half2float(h) * kF8WScale);          // exact unless |w| >= 2 (checked on the host side)
+        hi[i] = __float2half_rn(__half2float(h) * wscale);             // exact: |w| * 2^E < 2^15 (host picks E)
         uint8_t* blk = lo8 + (i - ci) * 2 + (size_t)(ci / 64) * 128;
-        blk[ci % 64] = to_e4m3(lo * kF8WScale);
-        blk[64 + ci % 64] = to_e4m3(v * kF8WHiScale);
+        blk[ci % 64] = to_e4m3(lo * (wscale * kF8WLoRel));
+        blk[64 + ci % 64] = to_e4m3(v * (wscale * kF8WRel));
     }
 }
 
@@ -161,6 +166,16 @@ __global__ void k_finalize_stats(const double* __restrict__ stats, const float* 
     ss[i] = make_float2(g * rstd, bt - (float)mean * g * rstd);
 }
 
+// Per-channel affine (eval-mode BatchNorm folded to scale / shift, or a conv bias) broadcast to the [n, c] table.
+__global__ void k_fill_ss(const float* __restrict__ scale, const float* __restrict__ shift, int n, int c, float2* __restrict__ ss)
+{
+    lwb::pdl_wait();
+    lwb::pdl_trigger();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * c) return;
+    ss[i] = make_float2(scale ? scale[i % c] : 1.f, shift ? shift[i % c] : 0.f);
+}
+
 // Plain (two-pass, fp64) statistics for tensors that did not come out of the conv epilogue.
 __global__ void __launch_bounds__(256) k_stats_nhwc(const float* __restrict__ x, int hw, int c, double* __restrict__ stats)
 {
@@ -197,6 +212,10 @@ struct NormActParams {
     const float* warp_src; int src_batch; const float* T; int th, tw, align_corners;
     float* y_f32; __half* y_hi; __half* y_lo;
     int lo_format;                                       // 0: y_lo = fp16 residual; 1: fp8 pair blocks (see kF8* above)
+    int* range_flag;                                     // |= 1 / 2 when an emitted operand leaves the f8 / fp16 range
+    // EXT only (BatchNorm-style nets, networks/hmr.py): the operands are relu?(y * post_scale[c] + post_shift[c]) while
+    // y_f32 keeps y; the residual is read at (res_step*y, res_step*x) of a [n, h*res_step, w*res_step, c] tensor
+    const float* post_scale; const float* post_shift; int post_relu; int res_step;
 };
 
 // Block = 256 threads = (256 / groups) pixels x groups channel-octets, two pixel rounds per thread so
@@ -204,7 +223,7 @@ struct NormActParams {
 // computed once (by one thread) and shared through smem instead of once per channel octet.
 struct TapRec { int o00, m; float w00, w01, w10, w11; };
 
-template <bool WARP>
+template <bool WARP, bool EXT>
 __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
 {
     constexpr int R = 2;                                 // pixel rounds per thread
@@ -218,8 +237,8 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
     const long pix0 = (long)blockIdx.x * (ppb * R);
     __shared__ TapRec s_tap[512];                      // ppb * R <= 512 (c = 8)
     if (WARP) {
-        if (threadIdx.x < ppb * R) {
-            const long pg = pix0 + threadIdx.x;
+        for (int i = threadIdx.x; i < ppb * R; i += 256) {       // ppb * R = 512 when c == 8
+            const long pg = pix0 + i;
             TapRec t = {0, 0, 0.f, 0.f, 0.f, 0.f};
             if (pg < npix) {
                 const int b = (int)(pg / hw), pix = (int)(pg % hw);
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
                 lwb::make_taps(gx, gy, P.h, P.w, P.align_corners, tp);
                 t.o00 = tp.o00; t.m = tp.m; t.w00 = tp.w00; t.w01 = tp.w01; t.w10 = tp.w10; t.w11 = tp.w11;
             }
-            s_tap[threadIdx.x] = t;
+            s_tap[i] = t;
         }
         __syncthreads();
     }
@@ -253,7 +272,12 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
     if (P.residual) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const float4* src = reinterpret_cast<const float4*>(P.residual + off[r]);
+            size_t roff = off[r];
+            if (EXT && P.res_step > 1 && ok[r]) {
+                const int pix = (int)((pix0 + r * ppb + lp) % hw), y = pix / P.w, x = pix % P.w, st = P.res_step;
+                roff = (((size_t)bb[r] * (P.h * st) + (size_t)y * st) * (P.w * st) + (size_t)x * st) * P.c + g * 8;
+            }
+            const float4* src = reinterpret_cast<const float4*>(P.residual + roff);
             const float4 a = ok[r] ? __ldg(src) : make_float4(0, 0, 0, 0), c = ok[r] ? __ldg(src + 1) : make_float4(0, 0, 0, 0);
             res[r][0] = a.x; res[r][1] = a.y; res[r][2] = a.z; res[r][3] = a.w; res[r][4] = c.x; res[r][5] = c.y; res[r][6] = c.z; res[r][7] = c.w;
         }
@@ -302,11 +326,30 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
             o[1] = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
         }
         if (P.y_hi) {
+            if (EXT && P.post_scale) {
+                const float4* ps = reinterpret_cast<const float4*>(P.post_scale + g * 8);
+                const float4* pt = reinterpret_cast<const float4*>(P.post_shift + g * 8);
+                const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    v[r][k] = fmaf(v[r][k], sc[k], sh[k]);
+                    if (P.post_relu) v[r][k] = fmaxf(v[r][k], 0.f);
+                }
+            }
             __align__(16) __half hh[8];
             __align__(16) __half ll[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) split_half(v[r][k], hh[k], ll[k]);
-            *reinterpret_cast<uint4*>(P.y_hi + off[r]) = *reinterpret_cast<const uint4*>(hh);
+            const uint4 hv = *reinterpret_cast<const uint4*>(hh);
+            if (P.range_flag) {
+                // max |hi| of the eight fp16 values as integers (monotone in |x|; inf / NaN sort above everything)
+                unsigned m = __vmaxu2(__vmaxu2(hv.x & 0x7fff7fffu, hv.y & 0x7fff7fffu), __vmaxu2(hv.z & 0x7fff7fffu, hv.w & 0x7fff7fffu));
+                m = max(m & 0xffffu, m >> 16);
+                if (m >= 0x6400u) atomicOr(P.range_flag, m >= 0x7b53u ? 3 : 1);       // fp16 1024.0 / 60000
+            }
+            *reinterpret_cast<uint4*>(P.y_hi + off[r]) = hv;
             if (P.y_lo && P.lo_format == 0) {
                 *reinterpret_cast<uint4*>(P.y_lo + off[r]) = *reinterpret_cast<const uint4*>(ll);
             } else if (P.y_lo) {
@@ -314,7 +357,7 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
                 __align__(8) uint8_t l8[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    x8[k] = to_e4m3(v[r][k]);
+                    x8[k] = to_e4m3(v[r][k] * kF8XScale);
                     l8[k] = to_e4m3((v[r][k] - __half2float(hh[k])) * kF8XLoScale);
                 }
                 // channel c of this pixel lives in 64-channel block c / 64: bytes [c % 64] and [64 + c % 64]
@@ -335,15 +378,31 @@ __device__ __forceinline__ uint8_t to_u8(float x) {
     return (uint8_t)__float2int_rz(__fmul_rn(__fmul_rn(__fadd_rn(x, 1.f), 0.5f), 255.f));
 }
 
-__global__ void __launch_bounds__(256) k_heads(const float* __restrict__ raw, int n, int hw, int c_stride,
+// folded_kw > 0: ``raw`` is the output of the 7x7 heads run as a (kh x 1) tensor-core conv whose N dimension holds the
+// filter columns -- raw[y, x', kx*4 + co] = sum_{ky,c} in[y+ky-3, x', c] * w[co, c, ky, kx] -- and the filter row is summed here:
+//   out[y, x, co] = sum_kx raw[y, x + kx - kw/2, kx*4 + co]        (columns outside the image contribute the zero padding)
+__global__ void __launch_bounds__(256) k_heads(const float* __restrict__ raw, int n, int hw, int w, int c_stride, int folded_kw,
                                                const float* __restrict__ bg, int bg_batch,
                                                float* __restrict__ color, float* __restrict__ mask, float* __restrict__ pred,
                                                float* __restrict__ pred_hwc, uint8_t* __restrict__ pred_u8_bgr)
 {
+    lwb::pdl_wait();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)n * hw) return;
     const int b = (int)(i / hw), p = (int)(i % hw);
-    const float4 r = __ldg(reinterpret_cast<const float4*>(raw + (size_t)i * c_stride));
+    float4 r;
+    if (folded_kw > 0) {
+        const int x = p % w;
+        r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kx = 0; kx < folded_kw; kx++) {
+            const int xs = x + kx - folded_kw / 2;
+            if (xs < 0 || xs >= w) continue;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(raw + (size_t)(i + (xs - x)) * c_stride + kx * 4));
+            r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+        }
+    } else {
+        r = __ldg(reinterpret_cast<const float4*>(raw + (size_t)i * c_stride));
+    }
     const float col[3] = {tanhf(r.x), tanhf(r.y), tanhf(r.z)};
     const float m = 1.f / (1.f + expf(-r.w));
     if (mask) mask[i] = m;
@@ -422,13 +481,14 @@ extern "C" int lwb_pack_conv_weight(const float* w, int cout, int cin, int kh, i
 }
 
 extern "C" int lwb_pack_conv_weight_f8(const float* w, int cout, int cin, int kh, int kw, int transposed,
-                                       int cout_pad, int cin_pad, uint16_t* w_hi, uint8_t* w_lo8, lwb_stream_t stream)
+                                       int cout_pad, int cin_pad, int w_exp, uint16_t* w_hi, uint8_t* w_lo8, lwb_stream_t stream)
 {
     LWB_CHECK_ARG(w && w_hi && w_lo8, "null pointer");
     LWB_CHECK_ARG(cout > 0 && cin > 0 && kh > 0 && kw > 0 && cout_pad >= cout && cin_pad >= cin && (cin_pad % 64) == 0, "bad sizes");
+    LWB_CHECK_ARG(w_exp >= -40 && w_exp <= 60, "w_exp out of range");
     const long total = (long)kh * kw * cout_pad * cin_pad;
     k_pack_weight_f8<<<(int)min((total + 255) / 256, 4096l), 256, 0, (cudaStream_t)stream>>>(
-        w, cout, cin, kh, kw, transposed, cout_pad, cin_pad, (__half*)w_hi, w_lo8);
+        w, cout, cin, kh, kw, transposed, cout_pad, cin_pad, ldexpf(1.f, w_exp), (__half*)w_hi, w_lo8);
     LWB_LAUNCH_OK();
     return LWB_OK;
 }
@@ -485,20 +545,33 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
                                  const float* residual,
                                  const float* warp_src, int src_batch, const float* T, int th, int tw, int align_corners,
                                  float* scale_shift_ws,
-                                 float* y_f32, uint16_t* y_hi, uint16_t* y_lo, int lo_format, lwb_stream_t stream)
+                                 float* y_f32, uint16_t* y_hi, uint16_t* y_lo, int lo_format,
+                                 const float* post_scale, const float* post_shift, int post_relu, int res_step,
+                                 int* range_flag, lwb_stream_t stream)
 {
     LWB_CHECK_ARG(lo_format == 0 || (lo_format == 1 && (c % 64) == 0), "lo_format 1 (fp8 pairs) needs channels in blocks of 64");
     LWB_CHECK_ARG(raw, "null pointer");
     LWB_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0, "channels must be a multiple of 8");
-    LWB_CHECK_ARG(!stats || scale_shift_ws, "stats needs the scale/shift workspace [n,c,2] f32");
+    const bool affine = !stats && (gamma || beta);       // no statistics: y = x * gamma[c] + beta[c] (folded BatchNorm / bias)
+    LWB_CHECK_ARG(!(stats || affine) || scale_shift_ws, "normalisation needs the scale/shift workspace [n,c,2] f32");
     LWB_CHECK_ARG(!warp_src || (T && th > 0 && tw > 0 && (src_batch == 1 || src_batch == n)), "bad warp arguments");
+    LWB_CHECK_ARG(!warp_src || c >= 16, "the warp variant needs at least 16 channels");
+    LWB_CHECK_ARG((post_scale == nullptr) == (post_shift == nullptr), "post_scale and post_shift go together");
+    LWB_CHECK_ARG(res_step >= 0 && res_step <= 8, "bad residual step");
+    if (res_step == 0) res_step = 1;
+    const bool ext = post_scale != nullptr || res_step > 1;
+    LWB_CHECK_ARG(!(ext && warp_src), "post-affine / strided residual are not combined with the warp");
     cudaStream_t st = (cudaStream_t)stream;
     if (stats) {
         LWB_CUDA_OK(lwb::launch_pdl(k_finalize_stats, dim3(lwb::ceil_div((long)n * c, 256)), dim3(256), 0, st,
                                     stats, gamma, beta, eps, n, c, 1.0 / ((double)h * w), (float2*)scale_shift_ws));
+    } else if (affine) {
+        LWB_CUDA_OK(lwb::launch_pdl(k_fill_ss, dim3(lwb::ceil_div((long)n * c, 256)), dim3(256), 0, st,
+                                    gamma, beta, n, c, (float2*)scale_shift_ws));
     }
     NormActParams P;
-    P.raw = raw; P.ss = stats ? (const float2*)scale_shift_ws : nullptr; P.relu = relu;
+    P.raw = raw; P.ss = (stats || affine) ? (const float2*)scale_shift_ws : nullptr; P.relu = relu;
+    P.range_flag = range_flag; P.post_scale = post_scale; P.post_shift = post_shift; P.post_relu = post_relu; P.res_step = res_step;
     P.n = n; P.h = h; P.w = w; P.c = c;
     P.residual = residual;
     P.warp_src = warp_src; P.src_batch = src_batch; P.T = T; P.th = th; P.tw = tw; P.align_corners = align_corners;
@@ -506,12 +579,13 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
     const int groups = c / 8;
     LWB_CHECK_ARG(groups <= 256 && 256 % groups == 0, "channels / 8 must divide 256");
     const long blocks = lwb::ceil_div((long)n * h * w, (256 / groups) * 2);
-    if (warp_src) LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<true>, dim3((unsigned)blocks), dim3(256), 0, st, P));
-    else          LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<false>, dim3((unsigned)blocks), dim3(256), 0, st, P));
+    if (warp_src) LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<true, false>, dim3((unsigned)blocks), dim3(256), 0, st, P));
+    else if (ext) LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<false, true>, dim3((unsigned)blocks), dim3(256), 0, st, P));
+    else          LWB_CUDA_OK(lwb::launch_pdl(k_norm_act<false, false>, dim3((unsigned)blocks), dim3(256), 0, st, P));
     return LWB_OK;
 }
 
-extern "C" int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride,
+extern "C" int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride, int folded_kw,
                                    const float* bg, int bg_batch,
                                    float* color, float* mask, float* pred,
                                    float* pred_hwc, uint8_t* pred_u8_bgr, lwb_stream_t stream)
@@ -520,9 +594,9 @@ extern "C" int lwb_heads_composite(const float* raw, int n, int h, int w, int c_
     LWB_CHECK_ARG(bg || (!pred && !pred_hwc && !pred_u8_bgr), "the composite outputs need bg");
     LWB_CHECK_ARG(n > 0 && h > 0 && w > 0 && c_stride >= 4 && (c_stride % 4) == 0, "bad sizes");
     LWB_CHECK_ARG(!bg || bg_batch == 1 || bg_batch == n, "bg_batch must be 1 or n");
-    k_heads<<<lwb::ceil_div((long)n * h * w, 256), 256, 0, (cudaStream_t)stream>>>(
-        raw, n, h * w, c_stride, bg, bg_batch, color, mask, pred, pred_hwc, pred_u8_bgr);
-    LWB_LAUNCH_OK();
+    LWB_CHECK_ARG(folded_kw >= 0 && (folded_kw == 0 || ((folded_kw & 1) && folded_kw * 4 <= c_stride)), "bad folded_kw");
+    LWB_CUDA_OK(lwb::launch_pdl(k_heads, dim3(lwb::ceil_div((long)n * h * w, 256)), dim3(256), 0, (cudaStream_t)stream,
+                                raw, n, h * w, w, c_stride, folded_kw, bg, bg_batch, color, mask, pred, pred_hwc, pred_u8_bgr));
     return LWB_OK;
 }
 

@@ -20,8 +20,9 @@ fallback: without the CUDA library the calls raise.
 
 Extensions over the reference (all optional): source features may have batch 1 while the target
 batch is B (torch's grid_sample cannot broadcast); ``LWB_PRECISION=fp16`` selects the
-single-pass "fast" mode (the default ``fp16f8`` and ``fp16x3`` both meet the 1e-3 parity bar, see _split_mode); ``LWB_ALIGN_CORNERS=1``
-selects torch-1.2 grid_sample semantics (default 0 = installed-torch semantics = the oracle).
+single-pass "fast" mode (the default ``fp16f8`` and ``fp16x3`` both meet the 1e-3 parity bar, see _split_mode);
+the LWB's grid_sample follows the reference's pinned torch 1.2 (align_corners=True), ``LWB_ALIGN_CORNERS=0``
+selects what torch >= 1.3 does for the same flag-less call (kernels.default_align_corners).
 """
 import os
 
@@ -39,12 +40,27 @@ def precision_mode():
     return os.environ.get("LWB_PRECISION", DEFAULT_PRECISION)
 
 
-def _split_mode():
+def _tc_heads():
+    """LWB_TC_HEADS (default 1): the 7x7 output heads run on the tensor cores as a 7x1 filter whose N dimension
+    carries the 7 filter columns x 4 head channels (28 -> 32); the composite kernel sums the columns.  0 = the fp32
+    CUDA-core kernel (k_heads7x7)."""
+    return os.environ.get("LWB_TC_HEADS", "1") != "0"
+
+
+def fold_head_weights(w_img, w_att):
+    """[3,64,7,7] + [1,64,7,7] -> [32, 64, 7, 1]: output channel kx*4 + co of the (7 x 1) filter = column kx of head co
+    (networks/generator.py:126-134; rows 28..31 are zero)."""
+    w4 = torch.cat([w_img, w_att], dim=0).float()                      # [4, C, ky, kx]
+    folded = w4.permute(3, 0, 1, 2).reshape(28, w4.shape[1], 7, 1)     # [kx*4+co, C, ky, 1]
+    return torch.cat([folded, torch.zeros(4, w4.shape[1], 7, 1, dtype=folded.dtype, device=folded.device)], dim=0).contiguous()
+
+
+def _split_mode(mod=None):
     """LWB_PRECISION -> operand split code of the conv engine (lwb_conv_desc.split):
     fp16x3 = 1: x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, all fp16 (3 MMAs per K step);
     fp16f8 = 2: x_hi*w_hi in fp16 + (x*w_lo, x_lo*w) in e4m3 at twice the rate (2 MMA-equivalents per K step);
     fp16   = 0: single pass (not parity-gated)."""
-    mode = precision_mode()
+    mode = (getattr(mod, '_lwb_precision', None) if mod is not None else None) or precision_mode()
     codes = {"fp16": 0, "fp16x3": 1, "fp16f8": 2}
     if mode not in codes:
         raise LwbError("LWB_PRECISION must be fp16x3, fp16f8 or fp16")
@@ -52,7 +68,7 @@ def _split_mode():
 
 
 def _align_corners():
-    return os.environ.get("LWB_ALIGN_CORNERS", "0") == "1"
+    return K.default_align_corners()
 
 
 def _halo_mode():
@@ -94,6 +110,44 @@ class NetworkBase(nn.Module):
         for m in self.modules():
             if hasattr(m, '_lwb_streams'):
                 m._lwb_streams = {}
+
+    def set_precision(self, mode):
+        """Pin this network (and its sub-networks) to an operand mode regardless of LWB_PRECISION (None = follow the env)."""
+        if mode not in (None, "fp16", "fp16x3", "fp16f8"):
+            raise LwbError("precision must be fp16x3, fp16f8, fp16 or None")
+        for m in self.modules():
+            if isinstance(m, NetworkBase):
+                m.__dict__['_lwb_precision'] = mode
+
+    def range_flags(self):
+        """-> list of int32[1] device tensors, one per live stream: bit 0 = an activation left the e4m3 correction
+        range (|x| >= 1024, fp16f8 precision degrades for those elements), bit 1 = the fp16 range (|x| >= 60000 / NaN)."""
+        flags = []
+        for m in self.modules():
+            for st in getattr(m, '_lwb_streams', {}).values():
+                flags.append(st.range_flag)
+        return flags
+
+    def range_flag_tensor(self):
+        """One int32 device scalar = OR over the live streams' flags (values are 0, 1 or 3, so max == OR); None if no
+        stream exists yet.  No host sync."""
+        flags = self.range_flags()
+        if not flags:
+            return None
+        if len(flags) == 1:
+            return flags[0]
+        return torch.stack([f.reshape(()) for f in flags]).amax().reshape(1)
+
+    def range_status(self):
+        """OR of range_flags() as a Python int (one device sync); streams reset their flag at the start of a pass."""
+        flags = self.range_flags()
+        if not flags:
+            return 0
+        bits = torch.stack([f.reshape(()) for f in flags]).cpu()
+        out = 0
+        for b in bits.tolist():
+            out |= int(b)
+        return out
 
     def load_state_dict(self, *args, **kwargs):
         out = super(NetworkBase, self).load_state_dict(*args, **kwargs)
@@ -141,7 +195,7 @@ class _Act(object):
 
 class _Layer(object):
     """conv (+ InstanceNorm params) bound to buffers: plan + stats slot."""
-    __slots__ = ("plan", "raw", "stats", "gamma", "beta", "w")
+    __slots__ = ("plan", "raw", "stats", "gamma", "beta", "w", "wsrc")
 
 
 class _StreamBase(object):
@@ -159,23 +213,25 @@ class _StreamBase(object):
         return self._raw[key]
 
     def _make_layer(self, conv, norm, x0, x1=None, stride=1, transposed=False, rowk=False, row_pitch=0, h=None, w=None,
-                    halo=False, weight=None, pad=None, n_tile=0):
+                    halo=False, weight=None, pad=None, n_tile=0, pad_w=None):
         L = _Layer()
         wt = (weight if weight is not None else conv.weight).detach()
+        L.wsrc = None
         if rowk:
             L.w = K.pack_conv_weight_rowk(wt, split=min(self.split, 1))       # the stem keeps the fp16 hi/lo input
             cout, kh, kw = wt.shape[0], wt.shape[2], wt.shape[3]
             d = K.make_conv_desc(self.B, h, w, 8, cout, kh, kw, stride=1, pad=kh // 2, split=min(self.split, 1),
                                  rowk=True, row_pitch=row_pitch, halo=halo)
         else:
-            L.w = K.pack_conv_weight(wt, transposed=transposed, split=self.split)
+            L.w = None
+            L.wsrc = (wt, transposed)                   # packed in _finalize (one max|w| sync for the whole stream)
             cout = wt.shape[1] if transposed else wt.shape[0]
             kh, kw = wt.shape[2], wt.shape[3]
             cin0 = x0[0].shape[3]
             cin1 = x1[0].shape[3] if x1 is not None else 0
             d = K.make_conv_desc(self.B, h, w, cin0, cout, kh, kw, stride=stride,
                                  pad=(pad if pad is not None else conv.padding[0]),
-                                 cin1=cin1, transposed=transposed, split=self.split, halo=halo, n_tile=n_tile)
+                                 cin1=cin1, transposed=transposed, split=self.split, halo=halo, n_tile=n_tile, pad_w=pad_w)
         L.raw = self._raw_buf(d.h_out, d.w_out, cout)
         L.stats = (len(self._stats_slots), cout)
         self._stats_slots.append(cout)
@@ -187,8 +243,20 @@ class _StreamBase(object):
 
     def _finalize(self):
         cmax = max(max(self._stats_slots), 16)
-        self.stats = torch.zeros((len(self._stats_slots), self.B, cmax, 2), dtype=torch.float64, device=self.dev)
+        # InstanceNorm statistics of every layer + the operand-range flag share one buffer: one fill per pass
+        nstat = len(self._stats_slots) * self.B * cmax * 2
+        self._zero = torch.zeros(nstat * 8 + 8, dtype=torch.uint8, device=self.dev)
+        self.stats = self._zero[:nstat * 8].view(torch.float64).view(len(self._stats_slots), self.B, cmax, 2)
+        self.range_flag = self._zero[nstat * 8:nstat * 8 + 4].view(torch.int32)
         self.ws = torch.empty((self.B, cmax, 2), dtype=torch.float32, device=self.dev)
+        pend = [L for L in self._layers if L.wsrc is not None]
+        if pend:
+            amax = [None] * len(pend)
+            if self.split == 2:                         # per-layer weight exponent of the fp16f8 packing: ONE host sync
+                amax = torch.stack([L.wsrc[0].abs().max().float() for L in pend]).tolist()
+            for L, a in zip(pend, amax):
+                L.w = K.pack_conv_weight(L.wsrc[0], transposed=L.wsrc[1], split=self.split, absmax=a)
+                L.wsrc = None
         for L in self._layers:
             slot, cout = L.stats
             # per-layer contiguous [B, cout, 2] view at the head of the slot (None: no norm follows)
@@ -197,10 +265,22 @@ class _StreamBase(object):
             d, x0, x1 = L.plan
             L.plan = K.ConvPlan(d, x0, x1, L.w, L.raw, L.stats)
 
+    def _label_heads(self):
+        """The folded heads issue N = 32 columns; their algorithmic work is the 7x7 x 64 -> 4 convolution."""
+        L = getattr(self, 'head_layer', None)
+        if L is not None and getattr(self, 'folded_kw', 7) == 7 and L.plan.desc.kw == 1:
+            L.plan.flops = 2.0 * self.B * self.H * self.W * 49 * 64 * 4
+            L.plan.label = "H7x7 64->4 @%d (7x1 filter, N = 7 cols x 4)" % self.H
+
+    def begin_pass(self):
+        """Zero the InstanceNorm statistics and the range flag (one fill)."""
+        self._zero.zero_()
+
     def _conv_norm(self, L, out, relu, residual=None, warp_src=None, T=None, ac=False):
         L.plan.run()
         K.norm_act_nhwc(L.raw, L.stats, L.gamma, L.beta, relu, self.ws, residual=residual, warp_src=warp_src, T=T,
-                        align_corners=ac, y_f32=out.f32, y_hi=out.hi, y_lo=out.lo, lo_format=1 if self.split == 2 else 0)
+                        align_corners=ac, y_f32=out.f32, y_hi=out.hi, y_lo=out.lo, lo_format=1 if self.split == 2 else 0,
+                        range_flag=self.range_flag)
 
 
 class _UnetStream(_StreamBase):
@@ -249,7 +329,7 @@ class _UnetStream(_StreamBase):
             ld = self._make_layer(net.decoders[i][0], net.decoders[i][1], prev.pair, stride=2, transposed=True, h=h, w=w)
             c, h, w = c // 2, h * 2, w * 2
             last = (i == nd - 1)
-            tc_heads = (hm != '0')
+            tc_heads = (hm != '0') or (_tc_heads() and c == 64)
             out = _Act((B, h, w, c), dev, split, want_f32=(last and not tc_heads), want_half=(not last or tc_heads))
             ls = self._make_layer(net.skippers[i][0], net.skippers[i][1], self.e[nd - 1 - i].pair, x1=up.pair, h=h, w=w,
                                   halo=(hm != '0'))
@@ -259,7 +339,16 @@ class _UnetStream(_StreamBase):
             prev = out
         w_img, w_att = net.img_reg[0].weight.detach(), net.attetion_reg[0].weight.detach()
         self.head_layer = None
-        if hm != '0':
+        self.folded_kw = 0
+        if hm == '0' and _tc_heads() and c == 64:
+            # img_reg (64->3) + attetion_reg (64->1): a 7 x 1 filter with N = 7 columns x 4 channels (-> 32) on the tensor
+            # cores; the composite kernel adds the seven column partials of every pixel (lwb_heads_composite, folded_kw)
+            self.head_layer = self._make_layer(None, None, prev.pair, h=H, w=W, weight=fold_head_weights(w_img, w_att),
+                                               pad=3, pad_w=0, n_tile=32)
+            self._stats_slots[-1] = 0
+            self.head_raw = self.head_layer.raw
+            self.folded_kw = 7
+        elif hm != '0':
             # img_reg (64->3) + attetion_reg (64->1) as one 7x7 conv padded to 16 output channels on the
             # tensor cores (halo variant, N tile 16); channels 0..3 are consumed by the composite kernel
             w16 = torch.cat([w_img, w_att, torch.zeros(12, *w_img.shape[1:], device=w_img.device, dtype=w_img.dtype)], dim=0)
@@ -270,6 +359,7 @@ class _UnetStream(_StreamBase):
             self.w4 = K.pack_head_weights(w_img, w_att)
             self.head_raw = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
         self._finalize()
+        self._label_heads()
 
     # ---- pieces -------------------------------------------------------------------------
     def load_input(self, x):
@@ -279,7 +369,7 @@ class _UnetStream(_StreamBase):
 
     def encode(self, warp_srcs=None, T=None, ac=False, upto=None):
         """encoders 0..n_down; warp_srcs[i] (NHWC fp32, i >= 1) is LWB-added after encoder i."""
-        self.stats.zero_()
+        self.begin_pass()
         self._conv_norm(self.enc_layers[0], self.e[0], True)
         for i in range(1, self.n_down + 1):
             src = warp_srcs[i] if warp_srcs is not None else None
@@ -293,7 +383,8 @@ class _UnetStream(_StreamBase):
         if act.f32 is None:
             raise LwbError("second warp needs an fp32 activation")
         K.norm_act_nhwc(act.f32, None, None, None, False, self.ws, warp_src=src, T=T, align_corners=ac,
-                        y_f32=act.f32, y_hi=act.hi, y_lo=act.lo, lo_format=1 if self.split == 2 else 0)
+                        y_f32=act.f32, y_hi=act.hi, y_lo=act.lo, lo_format=1 if self.split == 2 else 0,
+                        range_flag=self.range_flag)
 
     def resnets(self, warp_srcs=None, T=None, ac=False):
         x = self.e[self.n_down]
@@ -317,7 +408,7 @@ class _UnetStream(_StreamBase):
             self.head_layer.plan.run()
         else:
             K.conv7x7_heads_nhwc(self.d_out[-1].f32, self.w4, out=self.head_raw)
-        return K.heads_composite(self.head_raw, bg, want_color=want_color, want_mask=want_mask, **out)
+        return K.heads_composite(self.head_raw, bg, want_color=want_color, want_mask=want_mask, folded_kw=self.folded_kw, **out)
 
     def encoder_outs_nchw(self):
         outs = []
@@ -371,26 +462,39 @@ class _ResnetStream(_StreamBase):
             i += 1
         for k in range(nd):
             last = (k == nd - 1)
-            out = _Act((B, h * 2, w * 2, c // 2), dev, split, want_f32=last, want_half=not last)
+            tc_heads = _tc_heads() and c // 2 == 64
+            out = _Act((B, h * 2, w * 2, c // 2), dev, split, want_f32=(last and not tc_heads), want_half=(not last or tc_heads))
             self.seq.append(("cn", self._make_layer(layers[i], layers[i + 1], prev.pair, stride=2, transposed=True, h=h, w=w), out, True, None))
             c, h, w = c // 2, h * 2, w * 2
             prev = out
             i += 3
         self.final = prev
         w_img = layers[i].weight.detach()
-        self.w4 = K.pack_head_weights(w_img, torch.zeros_like(w_img[:1]))
-        self.head_raw = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        self.head_layer = None
+        if _tc_heads() and c == 64:
+            self.head_layer = self._make_layer(None, None, prev.pair, h=H, w=W, pad=3, pad_w=0, n_tile=32,
+                                               weight=fold_head_weights(w_img, torch.zeros_like(w_img[:1])))
+            self._stats_slots[-1] = 0
+            self.head_raw = self.head_layer.raw
+        else:
+            self.w4 = K.pack_head_weights(w_img, torch.zeros_like(w_img[:1]))
+            self.head_raw = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
         self._finalize()
+        self._label_heads()
 
     def run(self, x):
         if tuple(x.shape) != (self.B, self.cin, self.H, self.W):
             raise LwbError("unexpected input shape %s" % (tuple(x.shape),))
         K.nchw_to_nhwc_split(x.float().contiguous(), c_pad=8, pad_hw=(3, 3, 3, 5), hi=self.x_pad.hi, lo=self.x_pad.lo)
-        self.stats.zero_()
+        self.begin_pass()
         for _, L, out, relu, res in self.seq:
             self._conv_norm(L, out, relu, residual=(res.f32 if res is not None else None))
-        K.conv7x7_heads_nhwc(self.final.f32, self.w4, out=self.head_raw)
-        color, _, _ = K.heads_composite(self.head_raw, None, want_color=True, want_mask=False)
+        if self.head_layer is not None:
+            self.head_layer.plan.run()
+        else:
+            K.conv7x7_heads_nhwc(self.final.f32, self.w4, out=self.head_raw)
+        color, _, _ = K.heads_composite(self.head_raw, None, want_color=True, want_mask=False,
+                                        folded_kw=7 if self.head_layer is not None else 0)
         return color
 
 
@@ -412,9 +516,11 @@ def profile_streams(warm_fn, run_fn):
 
 def _stream_for(mod, cls, key, *args, **kw):
     streams = mod.__dict__.setdefault('_lwb_streams', {})
-    if key not in streams:
-        if len(streams) >= 4:
-            streams.clear()
+    if key in streams:
+        streams[key] = streams.pop(key)                  # most recently used last
+    else:
+        while len(streams) >= 4:                         # evict the least recently used shape only (each holds ~GBs at B=16)
+            streams.pop(next(iter(streams)))
         streams[key] = cls(mod, *args, **kw)
     return streams[key]
 
@@ -465,7 +571,7 @@ class ResNetGenerator(NetworkBase):
             c = c.expand(c.size(0), c.size(1), x.size(2), x.size(3))
             x = torch.cat([x, c], dim=1)
         B, _, H, W = x.shape
-        split = _split_mode()
+        split = _split_mode(self)
         st = _stream_for(self, _ResnetStream, ('bg', B, H, W, split), B, H, W, x.device, split)
         return st.run(x)
 
@@ -521,7 +627,7 @@ class ResUnetGenerator(NetworkBase):
 
     def _stream(self, x, keep_f32, tag):
         B, _, H, W = x.shape
-        split = _split_mode()
+        split = _split_mode(self)
         return _stream_for(self, _UnetStream, (tag, B, H, W, split, keep_f32), B, H, W, x.device, split, keep_f32=keep_f32)
 
     @torch.no_grad()

@@ -107,7 +107,7 @@ class Imitator(object):
 
     @property
     def _ac(self):
-        return os.environ.get("LWB_ALIGN_CORNERS", "0") == "1"
+        return K.default_align_corners()
 
     def _details(self, smpl):
         if self.hmr is None:
@@ -155,6 +155,7 @@ class Imitator(object):
             src_info['bg'] = self.bgnet(img, masks=body_mask, only_x=True)
         ft_mask = 1 - morph(src_info['cond'][:, -1:, :, :], ks=getattr(self._opt, 'ft_ks', 3), mode='erode')
         src_inputs = torch.cat([img * ft_mask, src_info['cond']], dim=1)
+        src_info['src_inputs'] = src_inputs
         src_info['feats'] = self.generator.encode_src(src_inputs)
         self.src_info = src_info
         if visualizer is not None:
@@ -269,11 +270,14 @@ class Imitator(object):
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         pending = []
+        range_bits = [0]
 
         def drain(keep):
             while len(pending) > keep:
-                a0, b0, h_f, h_u8, done = pending.pop(0)
+                a0, b0, h_f, h_u8, h_flag, done = pending.pop(0)
                 done.synchronize()
+                if h_flag is not None:
+                    range_bits[0] |= int(h_flag[0])
                 host = h_u8 if as_uint8 else h_f
                 for j in range(b0 - a0):
                     outputs.append(host[j])
@@ -287,21 +291,43 @@ class Imitator(object):
             preds = self.forward(tsf_inputs, self.tsf_info['T'], host_layout=dict(hwc=not as_uint8, u8=want_u8))
             if visualizer is not None:
                 visualizer.vis_named_img('pred_' + cam_strategy, preds)
+            flag = self.generator.tsf_model.range_flag_tensor()            # operand-range bits of this chunk's pass
+            flag = flag.clone() if flag is not None else None              # snapshot: the next pass zeroes the live flag
             ready = torch.cuda.Event()
             ready.record(main)
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(ready)
                 h_f = self._to_host(self._out_hwc, sync=False) if not as_uint8 else None
                 h_u8 = self._to_host(self._out_u8, sync=False) if want_u8 else None
-                for t in (self._out_hwc, self._out_u8):
+                h_flag = self._to_host(flag, sync=False) if flag is not None else None
+                for t in (self._out_hwc, self._out_u8, flag):
                     if t is not None:
                         t.record_stream(self._copy_stream)
                 done = torch.cuda.Event()
                 done.record(self._copy_stream)
-            pending.append((a, b, h_f, h_u8, done))
+            pending.append((a, b, h_f, h_u8, h_flag, done))
             drain(keep=1)
         drain(keep=0)
         self._last_frame_info()
+        if range_bits[0] and not getattr(self, '_range_retry', False):
+            # Never silently: activations left the range in which the default fp16f8 operand split keeps its precision
+            # (|x| >= 1024: the e4m3 correction terms clip).  Pin the generator to fp16x3 (fp16 corrections, range 6e4)
+            # and redo the call; beyond the fp16 range nothing in this engine can represent the activations.
+            import warnings
+            if range_bits[0] & 2:
+                raise LwbError("generator activations exceed the fp16 range (|x| >= 6e4 or non-finite): the conv engine's "
+                               "fp16 operands cannot represent them")
+            warnings.warn("lwb_b200: activations beyond the fp16f8 correction range (|x| >= 1024); switching this "
+                          "generator to LWB_PRECISION=fp16x3 and recomputing the sequence")
+            self.generator.set_precision("fp16x3")
+            self._range_retry = True
+            try:
+                enc_in = self.src_info.get('src_inputs')
+                if enc_in is not None:
+                    self.src_info['feats'] = self.generator.encode_src(enc_in)
+                return self.inference(tgt_paths, tgt_smpls, cam_strategy, output_dir, visualizer, verbose, as_uint8)
+            finally:
+                self._range_retry = False
         return outputs
 
     @torch.no_grad()

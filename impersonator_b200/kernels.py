@@ -4,6 +4,7 @@ Each function checks devices/dtypes/contiguity, allocates outputs with torch (de
 torch's job), and calls the library on torch's current stream.  No arithmetic happens here.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -14,6 +15,16 @@ from ._lib import ConvDesc, LwbError, check, lib, ptr, stream, _chk_cuda
 # utils/nmr.py:177: eye = [0, 0, -(1/tan(30 deg) + 1)], cast to float32 by look_at.py:33
 EYE_Z = float(np.float32(-(1. / np.tan(np.radians(30)) + 1)))
 NEAR, FAR = 0.1, 100.0              # rasterize.py:10-11 defaults (what render_fim_wim really uses)
+
+
+
+def default_align_corners():
+    """grid_sample convention of the LWB / source-image warp.  The reference calls F.grid_sample without the flag
+    (networks/generator.py:313, models/imitator.py:259) under its pinned torch==1.2.0 (requirements.txt:6), where
+    that means align_corners=True; the released checkpoints were trained that way, so True is the default.
+    LWB_ALIGN_CORNERS=0 selects what torch >= 1.3 does for the same call."""
+    return os.environ.get("LWB_ALIGN_CORNERS", "1") == "1"
+
 
 _ws_cache = {}
 
@@ -97,7 +108,7 @@ def raster_forward_face_index_map(faces, face_index_map, weight_map, depth_map, 
     return face_index_map, weight_map, depth_map
 
 
-def correspond(cam, verts, face_idx, image_size, map_fn, src_p2verts, src_img=None, align_corners=False,
+def correspond(cam, verts, face_idx, image_size, map_fn, src_p2verts, src_img=None, align_corners=None,
                want_f2verts=False, near=NEAR, far=FAR, out=None):
     """Fused render_fim_wim + encode_fim + cal_bc_transform + image warp + concat (lwb_correspond).
 
@@ -105,6 +116,8 @@ def correspond(cam, verts, face_idx, image_size, map_fn, src_p2verts, src_img=No
             tsf_img / cond = channel views of tsf_inputs, f2verts f32[B,F,3,3] | None)
     """
     _chk_cuda(cam, verts, face_idx, map_fn, src_p2verts, src_img)
+    if align_corners is None:
+        align_corners = default_align_corners()
     B, V = verts.shape[:2]
     F = face_idx.shape[0]
     C = map_fn.shape[1]
@@ -136,9 +149,11 @@ def correspond(cam, verts, face_idx, image_size, map_fn, src_p2verts, src_img=No
     return out
 
 
-def warp_nchw(x, T, align_corners=False, out=None, accumulate=False):
+def warp_nchw(x, T, align_corners=None, out=None, accumulate=False):
     """transform / stn (networks/generator.py:303-320): x [Bs,C,h,w], T [B,TH,TW,2] -> [B,C,h,w]."""
     _chk_cuda(x, T, out)
+    if align_corners is None:
+        align_corners = default_align_corners()
     if x.dtype != torch.float32 or T.dtype != torch.float32:
         raise LwbError("warp expects float32")
     sb, C, h, w = x.shape
@@ -150,12 +165,32 @@ def warp_nchw(x, T, align_corners=False, out=None, accumulate=False):
     return out
 
 
-def pack_conv_weight(w, transposed=False, cout_pad=None, cin_pad=None, split=True):
+class PackedWeight(tuple):
+    """(hi, lo) operand tensors of one conv layer; ``w_exp`` = the power of two they were packed with (split = 2)."""
+    w_exp = 15
+
+    def __new__(cls, hi, lo, w_exp=15):
+        self = super(PackedWeight, cls).__new__(cls, (hi, lo))
+        self.w_exp = w_exp
+        return self
+
+
+def weight_exponent(absmax):
+    """Per-layer scale of the fp16f8 weight packing: E with absmax * 2^E in [2^14, 2^15) (15 for an all-zero layer)."""
+    import math
+    absmax = float(absmax)
+    if not (absmax > 0.0) or math.isinf(absmax) or math.isnan(absmax):
+        return 15
+    return max(-40, min(60, 15 - math.frexp(absmax)[1]))
+
+
+def pack_conv_weight(w, transposed=False, cout_pad=None, cin_pad=None, split=True, absmax=None):
     """OIHW / IOHW fp32 -> ([tap][cout_pad][cin_pad] fp16 hi, lo).  split: 0/False single, 1/True fp16 hi+lo,
-    2 fp16 hi (x 2^15) + fp8 pair blocks (lwb_pack_conv_weight_f8)."""
+    2 fp16 hi (x 2^w_exp) + fp8 pair blocks (lwb_pack_conv_weight_f8).  ``absmax`` = max|w| when the caller already
+    knows it (one host sync per network instead of one per layer); computed here otherwise."""
     _chk_cuda(w)
     if int(split) == 2:
-        return _pack_conv_weight_f8(w, transposed, cout_pad, cin_pad)
+        return _pack_conv_weight_f8(w, transposed, cout_pad, cin_pad, absmax)
     w = w.float().contiguous()
     if transposed:
         cin, cout, kh, kw = w.shape
@@ -167,10 +202,10 @@ def pack_conv_weight(w, transposed=False, cout_pad=None, cin_pad=None, split=Tru
     lo = torch.empty_like(hi) if split else None
     check(lib().lwb_pack_conv_weight(ptr(w), cout, cin, kh, kw, 1 if transposed else 0, cout_pad, cin_pad,
                                      ptr(hi), ptr(lo), stream()), "lwb_pack_conv_weight")
-    return hi, lo
+    return PackedWeight(hi, lo)
 
 
-def _pack_conv_weight_f8(w, transposed, cout_pad, cin_pad):
+def _pack_conv_weight_f8(w, transposed, cout_pad, cin_pad, absmax=None):
     w = w.float().contiguous()
     if transposed:
         cin, cout, kh, kw = w.shape
@@ -178,13 +213,12 @@ def _pack_conv_weight_f8(w, transposed, cout_pad, cin_pad):
         cout, cin, kh, kw = w.shape
     cout_pad = cout_pad or cout
     cin_pad = cin_pad or cin
-    if float(w.abs().max()) >= 1.99:
-        raise LwbError("fp16f8 mode packs weights x 2^15 in fp16: |w| must stay below 2 (use LWB_PRECISION=fp16x3)")
+    w_exp = weight_exponent(w.abs().max() if absmax is None else absmax)
     hi = torch.empty((kh * kw, cout_pad, cin_pad), dtype=torch.float16, device=w.device)
     lo = torch.empty_like(hi)                                   # same bytes, fp8 pair blocks inside
-    check(lib().lwb_pack_conv_weight_f8(ptr(w), cout, cin, kh, kw, 1 if transposed else 0, cout_pad, cin_pad,
+    check(lib().lwb_pack_conv_weight_f8(ptr(w), cout, cin, kh, kw, 1 if transposed else 0, cout_pad, cin_pad, w_exp,
                                         ptr(hi), ptr(lo), stream()), "lwb_pack_conv_weight_f8")
-    return hi, lo
+    return PackedWeight(hi, lo, w_exp)
 
 
 def pack_conv_weight_rowk(w, cout_pad=None, cpx=8, kxs=8, split=True):
@@ -197,7 +231,7 @@ def pack_conv_weight_rowk(w, cout_pad=None, cpx=8, kxs=8, split=True):
     lo = torch.empty_like(hi) if split else None
     check(lib().lwb_pack_conv_weight_rowk(ptr(w), cout, cin, kh, kw, cout_pad, cpx, kxs, ptr(hi), ptr(lo), stream()),
           "lwb_pack_conv_weight_rowk")
-    return hi, lo
+    return PackedWeight(hi, lo)
 
 
 def nchw_to_nhwc_split(x, c_pad=None, pad_hw=(0, 0, 0, 0), hi=None, lo=None, split=True):
@@ -234,6 +268,8 @@ class ConvPlan(object):
         """x0 / x1 / w: (hi, lo) tensor pairs (x1 may be None); out_raw fp32 NHWC; stats f64 [n,cout,2] or None."""
         self._keep = (x0, x1, w, out_raw, stats)
         self.desc = desc
+        if desc.split == 2:
+            desc.w_exp = int(getattr(w, "w_exp", 15))
         handle = ctypes.c_void_p()
         x1 = x1 or (None, None)
         check(lib().lwb_conv_plan_create(ctypes.byref(desc), ptr(x0[0]), ptr(x0[1]), ptr(x1[0]), ptr(x1[1]),
@@ -266,15 +302,15 @@ class ConvPlan(object):
 
 
 def make_conv_desc(n, h_in, w_in, cin0, cout, kh, kw, stride=1, pad=0, dil=1, cin1=0, transposed=False,
-                   split=True, rowk=False, row_pitch=0, n_tile=0, halo=False):
+                   split=True, rowk=False, row_pitch=0, n_tile=0, halo=False, pad_w=None):
     if transposed:
         h_out, w_out = 2 * h_in, 2 * w_in
     elif rowk:
         h_out, w_out = h_in, w_in
     else:
         h_out = (h_in + 2 * pad - dil * (kh - 1) - 1) // stride + 1
-        w_out = (w_in + 2 * pad - dil * (kw - 1) - 1) // stride + 1
-    return ConvDesc(n=n, h_in=h_in, w_in=w_in, h_out=h_out, w_out=w_out, cin0=cin0, cin1=cin1, cout=cout,
+        w_out = (w_in + 2 * (pad if pad_w is None else pad_w) - dil * (kw - 1) - 1) // stride + 1
+    return ConvDesc(w_exp=15, pad_w=-1 if pad_w is None else pad_w, n=n, h_in=h_in, w_in=w_in, h_out=h_out, w_out=w_out, cin0=cin0, cin1=cin1, cout=cout,
                     kh=kh, kw=kw, stride=stride, pad=pad, dil=dil, transposed=1 if transposed else 0,
                     split=int(split), rowk=1 if rowk else 0, row_pitch=row_pitch, n_tile=n_tile,
                     halo=1 if halo else 0)
@@ -290,23 +326,28 @@ def instance_stats_nhwc(x, stats=None):
 
 
 def norm_act_nhwc(raw, stats, gamma, beta, relu, ws, eps=1e-5, residual=None, warp_src=None, T=None,
-                  align_corners=False, y_f32=None, y_hi=None, y_lo=None, lo_format=0):
+                  align_corners=False, y_f32=None, y_hi=None, y_lo=None, lo_format=0,
+                  post_scale=None, post_shift=None, post_relu=False, res_step=1, range_flag=None):
     """InstanceNorm + ReLU + residual + LWB warp-add on an NHWC fp32 tensor (lwb_norm_act_nhwc).
-    lo_format 1: y_lo receives the fp8 pair blocks that split=2 conv plans consume."""
-    _chk_cuda(raw, stats, gamma, beta, residual, warp_src, T, ws, y_f32, y_hi, y_lo)
+    lo_format 1: y_lo receives the fp8 pair blocks that split=2 conv plans consume.  stats=None with gamma/beta: plain
+    per-channel affine (folded BatchNorm / bias); post_*: second affine (+ReLU) applied to the operands only;
+    res_step: subsampled residual; range_flag: int32[1] device tensor collecting the operand-range bits."""
+    _chk_cuda(raw, stats, gamma, beta, residual, warp_src, T, ws, y_f32, y_hi, y_lo, post_scale, post_shift, range_flag)
     n, h, w, c = raw.shape
     sb, th, tw = 0, 0, 0
     if warp_src is not None:
         sb = warp_src.shape[0]
         th, tw = T.shape[1:3]
-    _count(2 if stats is not None else 1)
+    _count(2 if (stats is not None or gamma is not None or beta is not None) else 1)
     per = 4 + (4 if residual is not None else 0) + (4 if y_f32 is not None else 0) \
         + (2 if y_hi is not None else 0) + (2 if y_lo is not None else 0)
     nbytes = n * h * w * c * per + (warp_src.numel() * 4 + n * h * w * 8 if warp_src is not None else 0)
     with _Prof("norm", nbytes, "%dx%d c%d%s%s" % (h, w, c, " +res" if residual is not None else "", " +warp" if warp_src is not None else "")):
         check(lib().lwb_norm_act_nhwc(ptr(raw), ptr(stats), ptr(gamma), ptr(beta), eps, 1 if relu else 0, n, h, w, c,
                                       ptr(residual), ptr(warp_src), sb, ptr(T), th, tw, 1 if align_corners else 0,
-                                      ptr(ws), ptr(y_f32), ptr(y_hi), ptr(y_lo), int(lo_format), stream()), "lwb_norm_act_nhwc")
+                                      ptr(ws), ptr(y_f32), ptr(y_hi), ptr(y_lo), int(lo_format),
+                                      ptr(post_scale), ptr(post_shift), 1 if post_relu else 0, int(res_step),
+                                      ptr(range_flag), stream()), "lwb_norm_act_nhwc")
 
 
 def pack_head_weights(w_img, w_att):
@@ -331,7 +372,7 @@ def conv7x7_heads_nhwc(x, w4, out=None):
 
 
 def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, mask=None, pred=None,
-                    want_pred=True, pred_hwc=None, pred_u8=None):
+                    want_pred=True, pred_hwc=None, pred_u8=None, folded_kw=0):
     """-> color, mask, pred (NCHW).  ``pred_hwc`` f32 [n,h,w,3] / ``pred_u8`` uint8 BGR [n,h,w,3]: caller-allocated
     output-path buffers filled by the same launch."""
     _chk_cuda(raw, bg, color, mask, pred, pred_hwc, pred_u8)
@@ -348,7 +389,7 @@ def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, m
             raise LwbError("output-path buffers must be [n,h,w,3] float32 / uint8")
     _count(1)
     with _Prof("heads", 0.0):
-        check(lib().lwb_heads_composite(ptr(raw), n, h, w, cs, ptr(bg), bg.shape[0] if bg is not None else 0,
+        check(lib().lwb_heads_composite(ptr(raw), n, h, w, cs, int(folded_kw), ptr(bg), bg.shape[0] if bg is not None else 0,
                                         ptr(color), ptr(mask), ptr(pred), ptr(pred_hwc), ptr(pred_u8), stream()),
               "lwb_heads_composite")
     return color, mask, pred

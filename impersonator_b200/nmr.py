@@ -135,8 +135,7 @@ class SMPLRenderer(nn.Module):
         """utils/nmr.py:506-546: keep visible faces' points, -2 elsewhere."""
         def get_vis(orig, fim):
             vis = torch.zeros_like(orig) - 2.0
-            ids = fim.unique()
-            ids = ids[ids >= 0].long()
+            ids = fim.unique()[1:].long()                 # utils/nmr.py:528: the first unique value is taken to be -1
             vis[ids] = orig[ids]
             return vis
         if f2pts.dim() == 4:
@@ -144,7 +143,7 @@ class SMPLRenderer(nn.Module):
         return get_vis(f2pts, fims)
 
     # ---- fused per-frame path -------------------------------------------------------------
-    def _correspond(self, cam, vertices, src_p2verts, src_img, want_f2verts=False, align_corners=False):
+    def _correspond(self, cam, vertices, src_p2verts, src_img, want_f2verts=False, align_corners=None):
         if not vertices.is_cuda:
             raise LwbError("SMPLRenderer runs on CUDA tensors only (no CPU fallback)")
         cam = cam.float().contiguous()
@@ -159,7 +158,7 @@ class SMPLRenderer(nn.Module):
                             align_corners=align_corners, want_f2verts=want_f2verts)
 
     @torch.no_grad()
-    def correspond(self, cam, vertices, src_p2verts, src_img=None, align_corners=False, want_f2verts=False):
+    def correspond(self, cam, vertices, src_p2verts, src_img=None, align_corners=None, want_f2verts=False):
         """One pass = render_fim_wim + encode_fim + cal_bc_transform + F.grid_sample(src_img, T) + cat
         (models/imitator.py:251-260).  src_p2verts [1|B,F,3,2], src_img [1|B,3,H,W].
         -> dict(fim, wim, cond, T, tsf_img, tsf_inputs[, f2verts])."""

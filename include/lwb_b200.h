@@ -105,10 +105,12 @@ int lwb_warp_nchw(const float* x, int src_batch, int channels, int h, int w,
 int lwb_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int transposed,
                          int cout_pad, int cin_pad, uint16_t* w_hi, uint16_t* w_lo, lwb_stream_t stream);
 /* Weights for the "fp16 + fp8" operand split (lwb_conv_desc.split = 2): w_hi [taps][cout_pad][cin_pad] fp16 holds
- * fp16(w) * 2^15; w_lo8 (same byte size) holds, per 64-input-channel block of 128 bytes, 64 x e4m3((w - fp16(w)) * 2^15)
- * followed by 64 x e4m3(w * 2^3).  |w| must stay below 2.  cin_pad % 64 == 0.  See DESIGN.md section 4. */
+ * fp16(w) * 2^w_exp; w_lo8 (same byte size) holds, per 64-input-channel block of 128 bytes,
+ * 64 x e4m3((w - fp16(w)) * 2^(w_exp+4)) followed by 64 x e4m3(w * 2^(w_exp-10)).  The caller picks the layer's w_exp
+ * with max|w| * 2^w_exp in [2^14, 2^15) (any weight magnitude packs; 15 for |w| in [0.5, 1)) and passes the same
+ * value in lwb_conv_desc.w_exp.  cin_pad % 64 == 0.  See DESIGN.md section 4. */
 int lwb_pack_conv_weight_f8(const float* w, int cout, int cin, int kh, int kw, int transposed,
-                            int cout_pad, int cin_pad, uint16_t* w_hi, uint8_t* w_lo8, lwb_stream_t stream);
+                            int cout_pad, int cin_pad, int w_exp, uint16_t* w_hi, uint8_t* w_lo8, lwb_stream_t stream);
 
 /* Row-K packing for the 7x7 stem: [ky][cout_pad][kxs*cpx], K index = kx*cpx + c (zero beyond kw / cin). */
 int lwb_pack_conv_weight_rowk(const float* w, int cout, int cin, int kh, int kw,
@@ -136,6 +138,8 @@ typedef struct lwb_conv_desc {
     int n_tile;               /* 0 = auto; else force the N tile (16/64/128/256, must divide cout) */
     int halo;                 /* 1 = halo variant (stride-1 'same' k x k convs and the row-K stem): the activation
                                  tile + halo is staged once per 64-channel chunk and every tap reads a shifted window */
+    int w_exp;                /* split = 2: the power of two the weights were packed with (lwb_pack_conv_weight_f8) */
+    int pad_w;                /* horizontal padding when it differs from pad (e.g. a 7x1 filter); -1 = same as pad */
 } lwb_conv_desc;
 
 /* A plan owns the TMA descriptors of one conv layer bound to fixed device buffers; creating it
@@ -170,13 +174,21 @@ int lwb_instance_stats_nhwc(const float* x, int n, int h, int w, int c, double* 
  * T [n,TH,TW,2] resized to (h,w) (generator.py:303-320).  scale_shift_ws: [n,c,2] f32 scratch.
  * Outputs (each nullable): y_f32 [n,h,w,c]; y_hi / y_lo fp16 [n,h,w,c].  c % 8 == 0.
  * lo_format 0: y_lo = fp16(y - y_hi).  lo_format 1 (c % 64 == 0; consumers are split = 2 conv plans): y_lo holds, per
- * pixel and 64-channel block of 128 bytes, 64 x e4m3(y) followed by 64 x e4m3((y - y_hi) * 2^12). */
+ * pixel and 64-channel block of 128 bytes, 64 x e4m3(y * 2^-4) followed by 64 x e4m3((y - y_hi) * 2^10).
+ * stats == NULL with gamma / beta given: plain per-channel affine y = x*gamma[c] + beta[c] (eval-mode BatchNorm folded,
+ * or a conv bias: networks/hmr.py:66-103).  post_scale / post_shift [c] (nullable): the OPERANDS (y_hi / y_lo) hold
+ * relu?(y*post_scale + post_shift) while y_f32 keeps y (pre-activation ResNets: the next block's bn1+relu).
+ * res_step s > 1: residual is [n, h*s, w*s, c] and is read at (s*y, s*x) (the subsampled identity shortcut, hmr.py:21-36).
+ * range_flag (nullable, device int, caller zero-fills): |= 1 when an emitted operand has |y| >= 1024 (the e4m3 correction
+ * terms clip: precision of those elements degrades towards single-pass fp16), |= 2 when |y| >= 60000 or not finite. */
 int lwb_norm_act_nhwc(const float* raw, const double* stats, const float* gamma, const float* beta,
                       float eps, int relu, int n, int h, int w, int c,
                       const float* residual,
                       const float* warp_src, int src_batch, const float* T, int th, int tw, int align_corners,
                       float* scale_shift_ws,
-                      float* y_f32, uint16_t* y_hi, uint16_t* y_lo, int lo_format, lwb_stream_t stream);
+                      float* y_f32, uint16_t* y_hi, uint16_t* y_lo, int lo_format,
+                      const float* post_scale, const float* post_shift, int post_relu, int res_step,
+                      int* range_flag, lwb_stream_t stream);
 
 /* 7x7 output heads of the generator (networks/generator.py:126-134): img_reg (64->3) and
  * attetion_reg (64->1) as ONE 64->4 convolution, x [n,h,w,64] fp32 NHWC, w4 [49][64][4] fp32
@@ -191,8 +203,11 @@ int lwb_conv7x7_heads_nhwc(const float* x, const float* w4, int n, int h, int w,
  * color [n,3,h,w], mask [n,1,h,w], pred [n,3,h,w] NCHW, each nullable.
  * Output path, each nullable: pred_hwc [n,h,w,3] fp32 = preds.permute(1,2,0) of
  * models/imitator.py:178-180; pred_u8_bgr [n,h,w,3] uint8 = the image cv_utils.save_cv2_img(normalize=True) hands to
- * cv2.imwrite (utils/cv_utils.py:23-36: RGB->BGR, ((x+1)/2*255) in fp32, truncated). */
-int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride,
+ * cv2.imwrite (utils/cv_utils.py:23-36: RGB->BGR, ((x+1)/2*255) in fp32, truncated).
+ * folded_kw = 0: raw[...,0:4] are the four head channels.  folded_kw = kw (7): raw is the output of the 7x7 heads run on
+ * the tensor cores as a kh x 1 filter whose N dimension carries the filter columns, raw[y,x',kx*4+co] (c_stride >= 4*kw);
+ * the row sum  out[y,x,co] = sum_kx raw[y, x+kx-kw/2, kx*4+co]  happens here, before tanh / sigmoid. */
+int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride, int folded_kw,
                         const float* bg, int bg_batch,
                         float* color, float* mask, float* pred,
                         float* pred_hwc, uint8_t* pred_u8_bgr, lwb_stream_t stream);

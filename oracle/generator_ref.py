@@ -10,7 +10,11 @@ The arithmetic lives in the installed torch 2.11 (conv2d / conv_transpose2d / in
 grid_sampler_2d / upsample_bilinear2d) -- the same library the reference modules call, so this
 restatement is validated by direct comparison with the imported reference modules
 (tests/golden/make_generator_golden.py, run where /root/reference exists) and by the committed
-golden slices tests/golden/generator_*.npz.  Tolerance vs the CUDA path: 1e-3 max-abs (BASELINE.json).
+golden slices tests/golden/generator*.npz.  Tolerance vs the CUDA path: 1e-3 max-abs (BASELINE.json).
+
+``align_corners`` of the LWB's F.grid_sample (networks/generator.py:313, called without the flag):
+True = the reference's pinned torch 1.2 semantics (default here and in the product); False = what the
+installed torch 2.11 does for the same call (opt-in, LWB_ALIGN_CORNERS=0 on the product side).
 """
 import torch
 import torch.nn.functional as F
@@ -90,13 +94,13 @@ def resize_trans(x, T):                             # generator.py:303-311
     return Ts.permute(0, 2, 3, 1)
 
 
-def stn(x, T, align_corners=False):                 # generator.py:312-315
+def stn(x, T, align_corners=True):                 # generator.py:312-315
     if x.shape[0] != T.shape[0]:
         x = x.expand(T.shape[0], -1, -1, -1)
     return F.grid_sample(x, T, mode='bilinear', padding_mode='zeros', align_corners=align_corners)
 
 
-def transform(x, T, align_corners=False):           # generator.py:317-320
+def transform(x, T, align_corners=True):           # generator.py:317-320
     return stn(x, resize_trans(x, T), align_corners)
 
 
@@ -105,7 +109,7 @@ def encode_src(src_inputs, sd, repeat_num=6):       # generator.py:213-214
 
 
 def inference(src_encoder_outs, src_resnet_outs, tsf_inputs, T, sd, repeat_num=6, n_down=3,
-              align_corners=False):                  # generator.py:277-301
+              align_corners=True):                  # generator.py:277-301
     tsf_x = unet_encoder(tsf_inputs, sd, 'tsf_model', 0)
     tsf_encoder_outs = [tsf_x]
     for i in range(1, n_down + 1):
@@ -120,7 +124,7 @@ def inference(src_encoder_outs, src_resnet_outs, tsf_inputs, T, sd, repeat_num=6
     return unet_regress(unet_decode(tsf_x, tsf_encoder_outs, sd, 'tsf_model', n_down), sd, 'tsf_model')
 
 
-def infer_front(src_inputs, tsf_inputs, T, sd, repeat_num=6, n_down=3, align_corners=False):   # :216-243
+def infer_front(src_inputs, tsf_inputs, T, sd, repeat_num=6, n_down=3, align_corners=True):   # :216-243
     src_x = unet_encoder(src_inputs, sd, 'src_model', 0)
     tsf_x = unet_encoder(tsf_inputs, sd, 'tsf_model', 0)
     src_outs, tsf_outs = [src_x], [tsf_x]
@@ -140,13 +144,13 @@ def infer_front(src_inputs, tsf_inputs, T, sd, repeat_num=6, n_down=3, align_cor
     return src_img, src_mask, tsf_img, tsf_mask
 
 
-def forward(bg_inputs, src_inputs, tsf_inputs, T, sd, repeat_num=6, align_corners=False):      # :204-211
+def forward(bg_inputs, src_inputs, tsf_inputs, T, sd, repeat_num=6, align_corners=True):      # :204-211
     img_bg = resnet_generator(bg_inputs, sd, 'bg_model', repeat_num, 3)
     return (img_bg,) + infer_front(src_inputs, tsf_inputs, T, sd, repeat_num, 3, align_corners)
 
 
 def swap(tsf_inputs, enc12, enc21, res12, res21, T12, T21, sd, repeat_num=6, n_down=3,
-         align_corners=False):                       # generator.py:245-275
+         align_corners=True):                       # generator.py:245-275
     tsf_x = unet_encoder(tsf_inputs, sd, 'tsf_model', 0)
     outs = [tsf_x]
     for i in range(1, n_down + 1):
@@ -160,7 +164,7 @@ def swap(tsf_inputs, enc12, enc21, res12, res21, T12, T21, sd, repeat_num=6, n_d
     return unet_regress(unet_decode(tsf_x, outs, sd, 'tsf_model', n_down), sd, 'tsf_model')
 
 
-def imitator_forward(bg_img, src_feats, tsf_inputs, T, sd, repeat_num=6, align_corners=False):
+def imitator_forward(bg_img, src_feats, tsf_inputs, T, sd, repeat_num=6, align_corners=True):
     """Imitator.forward (models/imitator.py:326-336, front_warp off)."""
     enc, res = src_feats
     color, mask = inference(enc, res, tsf_inputs, T, sd, repeat_num, 3, align_corners)

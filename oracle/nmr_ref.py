@@ -8,9 +8,18 @@ Follows, line by line (device-agnostic torch code of the reference with ``.cuda(
   utils/nmr.py:328-341    encode_fim  (map_fn[fim.long()], fim == -1 -> last row)
   utils/nmr.py:617-659    cal_bc_transform
   models/imitator.py:105-107  src p2verts = f2verts[..., :2] with y negated
+  utils/nmr.py:343-352    encode_front_fim;  utils/nmr.py:506-546  get_vis_f2pts
 The rasterizer itself is oracle/raster.py (C restatement / reference CUDA).
-Parity unpinned by any reference test: pinned here only by construction
-(the reference code is restated verbatim) -- tolerance for wim/cond/T is 1e-5.
+No reference TEST pins these, so the restatement is pinned to the reference's CODE:
+tests/golden/make_nmr_golden.py imports /root/reference/utils/nmr.py unmodified, calls the
+``SMPLRenderer`` methods above as unbound functions and asserts torch.equal against every function
+here; the committed tests/golden/nmr.npz carries those outputs to the CPU suite and the GPU box.
+Tolerance of the CUDA path vs this file: fim exact, wim/cond/T 1e-5.
+
+``align_corners``: the reference calls F.grid_sample without the flag (networks/generator.py:313,
+models/imitator.py:259) under its pinned torch==1.2.0 (requirements.txt:6), where that means
+align_corners=True -- the default here; False (= what the installed torch 2.11 does for the same
+call) is the opt-in.
 """
 import math
 
@@ -99,13 +108,24 @@ def cal_bc_transform(src_f2pts, dst_fims, dst_wims, image_size):   # utils/nmr.p
     return T.view(bs, image_size, image_size, 2)
 
 
-def grid_sample(x, T, align_corners=False):
+def get_vis_f2pts(f2pts, fims):                                # utils/nmr.py:506-546
+    def get_vis(orig_f2pts, fim):
+        vis_f2pts = torch.zeros_like(orig_f2pts) - 2.0
+        face_ids = fim.unique()[1:].long()                     # :528 drops the first unique value (assumed -1)
+        vis_f2pts[face_ids] = orig_f2pts[face_ids]
+        return vis_f2pts
+    if f2pts.dim() == 4:
+        return torch.stack([get_vis(f2pts[i], fims[i]) for i in range(f2pts.shape[0])], dim=0)
+    return get_vis(f2pts, fims)
+
+
+def grid_sample(x, T, align_corners=True):
     """F.grid_sample(x, T) as the reference calls it (no flag: networks/generator.py:313,
-    models/imitator.py:259).  Under the installed torch that is align_corners=False."""
+    models/imitator.py:259): align_corners=True under the reference's torch 1.2."""
     return F.grid_sample(x, T, mode='bilinear', padding_mode='zeros', align_corners=align_corners)
 
 
-def correspond(cam, vertices, faces_idx, map_fn, src_p2v, src_img, image_size, align_corners=False):
+def correspond(cam, vertices, faces_idx, map_fn, src_p2v, src_img, image_size, align_corners=True):
     """models/imitator.py:251-260 (transfer_params_by_smpl) for a batch of target frames whose
     source-side tables have batch 1: returns dict(fim, wim, cond, T, tsf_img, tsf_inputs, f2verts)."""
     bs = cam.shape[0]

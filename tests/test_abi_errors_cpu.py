@@ -18,7 +18,7 @@ def test_null_pointers_rejected(L):
     assert rc == -1 and b"null pointer" in L.lwb_last_error()
     rc = L.lwb_warp_nchw(None, 1, 1, 4, 4, None, 1, 4, 4, 0, None, 0, None)
     assert rc == -1
-    rc = L.lwb_norm_act_nhwc(None, None, None, None, 1e-5, 0, 1, 4, 4, 8, None, None, 0, None, 0, 0, 0, None, None, None, None, 0, None)
+    rc = L.lwb_norm_act_nhwc(None, None, None, None, 1e-5, 0, 1, 4, 4, 8, None, None, 0, None, 0, 0, 0, None, None, None, None, 0, None, None, 0, 1, None, None)
     assert rc == -1
 
 
@@ -29,9 +29,9 @@ def test_bad_sizes_rejected(L):
     rc = L.lwb_correspond(dummy, dummy, dummy, 4, 10, 10, 16, 0.1, 100.0, 2.7, dummy, 3, dummy, None, 3, 0,
                           dummy, dummy, dummy, None, None, dummy, None)
     assert rc == -1 and b"src_batch" in L.lwb_last_error()
-    rc = L.lwb_norm_act_nhwc(dummy, None, None, None, 1e-5, 0, 1, 4, 4, 12, None, None, 0, None, 0, 0, 0, None, None, None, None, 0, None)
+    rc = L.lwb_norm_act_nhwc(dummy, None, None, None, 1e-5, 0, 1, 4, 4, 12, None, None, 0, None, 0, 0, 0, None, None, None, None, 0, None, None, 0, 1, None, None)
     assert rc == -1 and b"multiple of 8" in L.lwb_last_error()
-    rc = L.lwb_norm_act_nhwc(dummy, None, None, None, 1e-5, 0, 1, 4, 4, 32, None, None, 0, None, 0, 0, 0, None, None, dummy, dummy, 1, None)
+    rc = L.lwb_norm_act_nhwc(dummy, None, None, None, 1e-5, 0, 1, 4, 4, 32, None, None, 0, None, 0, 0, 0, None, None, dummy, dummy, 1, None, None, 0, 1, None, None)
     assert rc == -1 and b"blocks of 64" in L.lwb_last_error()
     assert L.lwb_raster_workspace_bytes(0, 256, 10) == 0
     assert L.lwb_raster_workspace_bytes(2, 256, 100) == 2 * 256 * 256 * 8 + 16 + 2 * 100 * 4

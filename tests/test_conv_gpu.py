@@ -63,13 +63,16 @@ def q8(t):
 
 
 def emulate_f8(x, w, conv):
-    """The arithmetic the fp16f8 mode is meant to perform, in float64 on the CPU."""
+    """The arithmetic the fp16f8 mode is meant to perform, in float64 on the CPU:
+    per-layer weight scale 2^E with max|w| * 2^E in [2^14, 2^15); x8 = e4m3(x / 16), xlo8 = e4m3(x_lo * 2^10),
+    wlo8 = e4m3(w_lo * 2^(E+4)), w8 = e4m3(w * 2^(E-10))."""
+    E = K.weight_exponent(w.abs().max())
     xh = x.half().double()
     wh = w.half().double()
     xl, wl = x.double() - xh, w.double() - wh
     main = conv(xh, wh)
-    t2 = conv(q8(x), q8((wl * 32768).float())) / 32768
-    t3 = conv(q8((xl * 4096).float()), q8(w * 8)) / 32768
+    t2 = conv(q8(x / 16), q8((wl * 2.0 ** (E + 4)).float())) / 2.0 ** E
+    t3 = conv(q8((xl * 1024).float()), q8(w * 2.0 ** (E - 10))) / 2.0 ** E
     return (main + t2 + t3).float()
 
 

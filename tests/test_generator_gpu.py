@@ -125,3 +125,59 @@ def test_both_parity_modes_meet_the_bar(cuda, net, monkeypatch, mode):
         dd = np.abs(sl(t) - g["fwd_" + name]).max()
         print("%s forward %-9s vs reference golden: %.3e" % (mode, name, dd))
         assert dd < TOL
+
+
+def test_align_corners_opt_in_matches_installed_torch_golden(cuda, net, monkeypatch):
+    """LWB_ALIGN_CORNERS=0: the flag-less F.grid_sample of the reference as torch >= 1.3 evaluates it (ac0_* goldens:
+    the reference modules run unpatched under the installed torch)."""
+    n, sd = net
+    monkeypatch.setenv("LWB_ALIGN_CORNERS", "0")
+    g = np.load(os.path.join(GOLD, "generator.npz"))
+    inp = S.synthetic_generator_inputs(1, 256, seed=11)
+    outs = n(inp["bg"].to(cuda), inp["src"].to(cuda), inp["tsf"].to(cuda), inp["T"].to(cuda))
+    for name, t in zip(("img_bg", "src_img", "src_mask", "tsf_img", "tsf_mask"), outs):
+        d = np.abs(sl(t) - g["ac0_fwd_" + name]).max()
+        print("align_corners=0 forward %-9s vs reference golden: %.3e" % (name, d))
+        assert d < TOL
+    # and the two conventions really differ on the warped stream
+    assert np.abs(g["fwd_tsf_img"] - g["ac0_fwd_tsf_img"]).max() > 1e-2
+
+
+@pytest.mark.parametrize("tag,B,size,seed,step", [("b16_256", 16, 256, 61, 16), ("b8_512", 8, 512, 71, 32)])
+def test_baseline_sizes_match_reference_golden(cuda, net, tag, B, size, seed, step):
+    """BASELINE configs[2] (batch 16 @256) and configs[4] (batch 8 @512): encode_src + inference against slices and
+    per-frame means of what the REFERENCE modules produced at those sizes (tests/golden/generator_big.npz)."""
+    n, sd = net
+    g = np.load(os.path.join(GOLD, "generator_big.npz"))
+    inp = S.synthetic_generator_inputs(B, size, seed=seed)
+    enc, res = n.encode_src(inp["src"].to(cuda))
+    img, mask = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda))
+    torch.cuda.synchronize()
+    d_img = np.abs(img[:, :, 3::step, 5::step].cpu().numpy() - g[tag + "_img"]).max(axis=(1, 2, 3))
+    d_mask = np.abs(mask[:, :, 3::step, 5::step].cpu().numpy() - g[tag + "_mask"]).max(axis=(1, 2, 3))
+    d_mean = np.abs(img.mean(dim=(1, 2, 3)).cpu().numpy() - g[tag + "_img_mean"])
+    d_amean = np.abs(img.abs().mean(dim=(1, 2, 3)).cpu().numpy() - g[tag + "_img_absmean"])
+    print("%s per-frame max-abs vs reference golden: img %s mask %s; means %.2e %.2e"
+          % (tag, np.array2string(d_img, precision=1), np.array2string(d_mask, precision=1), d_mean.max(), d_amean.max()))
+    assert d_img.shape[0] == B
+    assert d_img.max() < TOL and d_mask.max() < TOL              # every one of the B frames
+    assert d_mean.max() < 1e-4 and d_amean.max() < 1e-4
+    assert n.range_status() == 0
+
+
+def test_tensor_core_heads_equal_cuda_core_heads(cuda, net, monkeypatch):
+    """The 7x7 heads folded onto the tensor cores (7x1 filter, N = 7 columns x 4 channels) against the fp32 CUDA-core kernel."""
+    n, sd = net
+    inp = S.synthetic_generator_inputs(2, 256, seed=21)
+    enc, res = n.encode_src(inp["src"].to(cuda))
+    monkeypatch.setenv("LWB_TC_HEADS", "1")
+    n._lwb_invalidate()
+    img1, mask1 = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda))
+    img1, mask1 = img1.clone(), mask1.clone()
+    monkeypatch.setenv("LWB_TC_HEADS", "0")
+    n._lwb_invalidate()
+    img0, mask0 = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda))
+    d = max((img1 - img0).abs().max().item(), (mask1 - mask0).abs().max().item())
+    print("tensor-core heads vs CUDA-core heads: %.3e" % d)
+    n._lwb_invalidate()
+    assert d < 2e-4

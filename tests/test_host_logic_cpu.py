@@ -73,8 +73,9 @@ def test_synthetic_smpl_model_has_the_pickle_layout():
 def test_oracle_self_correspondence_is_the_identity_warp():
     """Domain round trip (size independent): a frame corresponded with ITSELF must give T = pixel-centre coordinates on
     every covered pixel (cal_bc_transform, utils/nmr.py:617-659, inverts the rasterizer's barycentrics) and therefore
-    warp the source image onto itself; uncovered pixels keep -2.  Pins the oracle's conventions (y flip, row flip,
-    align_corners=False sampling) without any golden file."""
+    warp the source image onto itself; uncovered pixels keep -2.  Pins the oracle's conventions (y flip, row flip)
+    without any golden file.  The image identity needs sampling at pixel centres (align_corners=False); the reference's
+    torch-1.2 convention (the default elsewhere) samples up to half a pixel off, as it did upstream."""
     from oracle import nmr_ref
     size = 128
     v, f = S.uv_sphere()
@@ -84,7 +85,7 @@ def test_oracle_self_correspondence_is_the_identity_warp():
     gx, gy = (2 * xs + 1 - size) / size, (2 * ys + 1 - size) / size
     src = torch.stack([torch.sin(3 * gx) * torch.cos(2 * gy), gx * gy, torch.cos(4 * gx + gy)])[None]
     f2v, fim, _ = nmr_ref.render_fim_wim(cam, verts, f, size)
-    out = nmr_ref.correspond(cam, verts, f, tabs["map_fn"], nmr_ref.src_p2verts(f2v), src, size)
+    out = nmr_ref.correspond(cam, verts, f, tabs["map_fn"], nmr_ref.src_p2verts(f2v), src, size, align_corners=False)
     cov = fim[0] >= 0
     assert 0.05 < cov.float().mean() < 0.6
     T = out["T"][0]
@@ -92,3 +93,12 @@ def test_oracle_self_correspondence_is_the_identity_warp():
     assert torch.all(T[~cov] == -2)
     assert (out["tsf_img"][0] - src[0])[:, cov].abs().max() < 2e-3
     assert torch.all(out["tsf_img"][0][:, ~cov] == 0)
+
+
+def test_weight_exponent_rule():
+    """Per-layer scale of the fp16f8 weight packing: max|w| * 2^E in [2^14, 2^15) for any magnitude."""
+    from impersonator_b200 import kernels as K
+    for a, e in ((1.5, 14), (0.99, 15), (0.5, 15), (0.02, 20), (2.0, 13), (5.0, 12), (0.0, 15)):
+        assert K.weight_exponent(a) == e, (a, K.weight_exponent(a))
+        if a > 0:
+            assert 2 ** 14 <= a * 2.0 ** e < 2 ** 15

@@ -80,6 +80,57 @@ def test_imitator_inference_matches_oracle(cuda):
     assert im.tsf_info["T"].shape[0] == 1                                    # tsf_info describes the last frame
 
 
+def test_imitator_batch16_every_frame_matches_oracle(cuda):
+    """The headline configuration (BASELINE configs[2]): batch_size = 16, ONE chunk of 16 frames through
+    Imitator.inference_by_smpls, every frame compared with the oracle's per-frame loop."""
+    torch.set_grad_enabled(False)
+    size, nf = 256, 16
+    v, f = S.uv_sphere()
+    tabs = S.synthetic_tables()
+    net = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    sd = S.fill_state_dict(net.state_dict(), seed=0)
+    net.load_state_dict(sd)
+    render = SMPLRenderer(image_size=size, faces=f.numpy(), map_fn=tabs["map_fn"])
+    body = SyntheticBodyModel(v)
+    opt = Opt()
+    opt.batch_size = 16
+    im = Imitator(opt, generator=net, hmr=body, render=render, device=cuda)
+    src_img = S.synthetic_source(size)
+    src_theta = np.zeros(85, np.float32)
+    src_theta[0], src_theta[3], src_theta[4] = 0.95, -0.4, 0.05
+    im.personalize("", src_smpl=src_theta, src_img=src_img)
+    g = torch.Generator().manual_seed(16)
+    tgt = np.zeros((nf, 85), np.float32)
+    tgt[:, 0] = 0.8 + 0.3 * torch.rand(nf, generator=g).numpy()
+    tgt[:, 1:3] = (torch.rand(nf, 2, generator=g).numpy() * 2 - 1) * 0.1
+    tgt[:, 3] = (torch.rand(nf, generator=g).numpy() * 2 - 1) * 3.0
+    tgt[:, 4] = (torch.rand(nf, generator=g).numpy() * 2 - 1) * 0.3
+    outs = im.inference_by_smpls(list(tgt), cam_strategy="smooth")
+    assert len(outs) == nf
+
+    sth = torch.from_numpy(src_theta)[None]
+    sinfo = body.get_details(sth)
+    f2v, sfim, _ = nmr_ref.render_fim_wim(sinfo["cam"], sinfo["verts"], f, size)
+    cond = nmr_ref.encode_fim(sfim, tabs["map_fn"])
+    p2v = nmr_ref.src_p2verts(f2v)
+    bg_mask = ref_morph(cond[:, -1:], 13, 'erode')
+    bg = G.resnet_generator(torch.cat([src_img * bg_mask, bg_mask], dim=1), sd, 'bg_model')
+    ft_mask = 1 - ref_morph(cond[:, -1:], 3, 'erode')
+    feats = G.encode_src(torch.cat([src_img * ft_mask, cond], dim=1), sd)
+    first_cam = torch.from_numpy(tgt[0:1, 0:3])
+    per_frame = []
+    for t in range(nf):
+        th = torch.from_numpy(tgt[t:t + 1])
+        cam = sinfo["cam"].clone()
+        cam[:, 1:] += th[:, 1:3] - first_cam[:, 1:]
+        tsf = body.get_details(torch.cat([cam, th[:, 3:75], sinfo["shape"]], dim=1))
+        c = nmr_ref.correspond(tsf["cam"], tsf["verts"], f, tabs["map_fn"], p2v, src_img, size)
+        pred, _, _ = G.imitator_forward(bg, feats, c["tsf_inputs"], c["T"], sd)
+        per_frame.append(float(np.abs(outs[t] - pred[0].permute(1, 2, 0).numpy()).max()))
+    print("Imitator batch 16 vs oracle loop, per-frame max-abs:", ["%.1e" % d for d in per_frame])
+    assert max(per_frame) < 1e-3
+
+
 def test_imitator_from_smpl_vectors_through_lbs_kernels(cuda):
     """85-float SMPL vectors in, frames out, with the SMPL LBS kernels as the body model (HumanModelRecovery.get_details,
     networks/hmr.py:302-330).  LBS parity itself is tests/test_smpl_gpu.py; here the oracle loop consumes the vertices the

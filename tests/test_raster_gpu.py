@@ -166,7 +166,9 @@ def test_correspond_source_pass_matches_render_fim_wim(cuda):
 
 def test_self_correspondence_is_the_identity_warp(cuda):
     """Round trip through lwb_correspond at the full 256^2 / 512^2 sizes: frame 0 corresponded with itself gives
-    T = pixel centres and tsf_img = src_img on covered pixels, -2 / 0 elsewhere (no oracle involved)."""
+    T = pixel centres and tsf_img = src_img on covered pixels, -2 / 0 elsewhere (no oracle involved).  The image identity
+    holds in the align_corners=False sampling convention (pixel centres are the rasterizer's sample points); the default
+    torch-1.2 convention shifts the sample by <= half a pixel, exactly as the reference did."""
     v, f = S.uv_sphere()
     tabs = S.synthetic_tables()
     for size in (256, 512):
@@ -179,7 +181,7 @@ def test_self_correspondence_is_the_identity_warp(cuda):
         src_pass = r.correspond(cam[:1].to(cuda), verts[:1].to(cuda), None, None, want_f2verts=True)     # personalize side
         p2v = src_pass["f2verts"][:, :, :, 0:2].clone()
         p2v[:, :, :, 1] *= -1                                                  # models/imitator.py:105-107
-        out = r.correspond(cam.to(cuda), verts.to(cuda), p2v.contiguous(), src.to(cuda))
+        out = r.correspond(cam.to(cuda), verts.to(cuda), p2v.contiguous(), src.to(cuda), align_corners=False)
         torch.cuda.synchronize()
         fim, T, img = out["fim"][0].cpu(), out["T"][0].cpu(), out["tsf_img"][0].cpu()
         cov = fim >= 0

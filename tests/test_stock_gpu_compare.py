@@ -14,10 +14,8 @@ from impersonator_b200.nmr import SMPLRenderer
 from oracle import generator_ref as G
 from oracle import nmr_ref, raster
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("LWB_RUN_STOCK") != "1",
-                                 reason="takes ~2.5 min (cuDNN builds its execution plans at first use of every conv shape); "
-                                        "run with LWB_RUN_STOCK=1 -- tools/gpu_final.sh does, result in profiles/r01/stock_compare.json")]
+pytestmark = pytest.mark.gpu
+FULL = os.environ.get("LWB_RUN_STOCK") == "1"      # also the TF32 leg and the reference rasterizer kernels (~2 min more)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -55,23 +53,26 @@ def test_stock_torch_and_reference_kernels_vs_this_library(cuda):
     torch.backends.cudnn.allow_tf32 = False                     # strict fp32 first: this run is also the parity reference
     torch.backends.cuda.matmul.allow_tf32 = False
     ref_img, ref_mask = G.inference(enc_b, res_b, tsf, T, sd_gpu)
-    out["stock_generator_ms_fp32"] = timeit(lambda: G.inference(enc_b, res_b, tsf, T, sd_gpu))
-    torch.backends.cudnn.allow_tf32 = True                      # torch's default on Ampere+
-    torch.backends.cuda.matmul.allow_tf32 = True
-    tf_img, _ = G.inference(enc_b, res_b, tsf, T, sd_gpu)
-    out["stock_generator_ms_tf32"] = timeit(lambda: G.inference(enc_b, res_b, tsf, T, sd_gpu))
-    out["stock_tf32_vs_stock_fp32_max_abs"] = (tf_img - ref_img).abs().max().item()
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    out["stock_generator_ms_fp32"] = timeit(lambda: G.inference(enc_b, res_b, tsf, T, sd_gpu), iters=3, warm=1)
+    if FULL:
+        torch.backends.cudnn.allow_tf32 = True                  # torch's default on Ampere+
+        torch.backends.cuda.matmul.allow_tf32 = True
+        tf_img, _ = G.inference(enc_b, res_b, tsf, T, sd_gpu)
+        out["stock_generator_ms_tf32"] = timeit(lambda: G.inference(enc_b, res_b, tsf, T, sd_gpu))
+        out["stock_tf32_vs_stock_fp32_max_abs"] = (tf_img - ref_img).abs().max().item()
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
 
     enc, res = n.encode_src(src)
     out["lwb_generator_ms"] = timeit(lambda: n.inference(enc, res, tsf, T))
     img, mask = n.inference(enc, res, tsf, T)
-    out["lwb_vs_stock_fp32_max_abs"] = max((img - ref_img).abs().max().item(), (mask - ref_mask).abs().max().item())
-    assert out["lwb_vs_stock_fp32_max_abs"] < 1e-3
+    per_frame = torch.maximum((img - ref_img).abs().amax(dim=(1, 2, 3)), (mask - ref_mask).abs().amax(dim=(1, 2, 3)))
+    out["lwb_vs_stock_fp32_max_abs"] = per_frame.max().item()
+    out["lwb_vs_stock_fp32_per_frame"] = [round(v, 6) for v in per_frame.tolist()]
+    assert out["lwb_vs_stock_fp32_max_abs"] < 1e-3               # all 16 frames of the headline batch, every pixel
 
     # --- rasterizer: the reference's kernels vs k_face_raster ------------------------------------------------
-    if raster.gpu_ref_available():
+    if FULL and raster.gpu_ref_available():
         v, f = S.uv_sphere()
         cam, verts = S.synthetic_frames(B, seed=1234, base_verts=v)
         faces = nmr_ref.project_to_faces(cam, verts, f).to(cuda).contiguous()
