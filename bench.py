@@ -436,7 +436,21 @@ def main():
         tf_burst = peaks.get("bf16_tflops") or 1650.0
         hbm_peak = peaks.get("hbm_gbs") or 6650.0
         src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        prof = GEN.profile_streams(lambda: [step_device(i) for i in range(3)], lambda: [step_device(i) for i in range(6)])
+        # per-kernel CUDA events need the kernels serialised (as ncu does): the instrumented passes run with LWB_STREAMS=1
+        had_streams = os.environ.get("LWB_STREAMS")
+        os.environ["LWB_STREAMS"] = "1"
+        try:
+            prof = GEN.profile_streams(lambda: [step_device(i) for i in range(3)], lambda: [step_device(i) for i in range(6)])
+            ms_serial, _ = timed(step_device, args.steps, 3, collective=False)
+        finally:
+            if had_streams is None:
+                os.environ.pop("LWB_STREAMS", None)
+            else:
+                os.environ["LWB_STREAMS"] = had_streams
+        line["streams"] = {"LWB_STREAMS": os.environ.get("LWB_STREAMS", "1"),
+                           "ms_per_step_single_stream": ms_serial / args.steps,
+                           "note": "roofline / breakdown / layers are measured with the kernels serialised (one stream), like ncu; "
+                                   "value / e2e use LWB_STREAMS sub-batches whose kernels overlap"}
         conv = prof["conv"]
         issue_units = {"fp16x3": 3.0, "fp16f8": 2.0, "fp16": 1.0}[mode]
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12

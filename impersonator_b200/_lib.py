@@ -61,6 +61,11 @@ SIGNATURES = {
     "lwb_smpl_workspace_bytes": (_sz, [_i]),
     "lwb_smpl_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lwb_gated_act_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "lwb_self_attention_nhwc": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "lwb_maxpool_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "lwb_global_avgpool_nhwc": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "lwb_linear": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "lwb_conv2d_direct_nchw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 

@@ -40,6 +40,19 @@ def precision_mode():
     return os.environ.get("LWB_PRECISION", DEFAULT_PRECISION)
 
 
+def _sub_batches(B, enc_w, res_w, bg):
+    """LWB_STREAMS (default 1): number of concurrent sub-batches ImpersonatorGenerator.inference splits a batch into.
+    Only when the source features / background are shared by the batch (the imitation case) and B divides evenly."""
+    try:
+        n = int(os.environ.get("LWB_STREAMS", "1"))
+    except ValueError:
+        n = 1
+    if n <= 1 or B % n or B // n < 2:
+        return 1
+    shared = all(t is None or t.shape[0] == 1 for t in list(enc_w) + list(res_w)) and (bg is None or bg.shape[0] == 1)
+    return n if shared else 1
+
+
 def _tc_heads():
     """LWB_TC_HEADS (default 1): the 7x7 output heads run on the tensor cores as a 7x1 filter whose N dimension
     carries the 7 filter columns x 4 head channels (28 -> 32); the composite kernel sums the columns.  0 = the fp32
@@ -719,18 +732,60 @@ class ImpersonatorGenerator(NetworkBase):
         (caller-allocated [B,H,W,3] float32 / uint8-BGR) receive the same frames in the layouts of the output
         path (models/imitator.py:178-180, utils/cv_utils.py:23-36) from that launch."""
         ac = _align_corners()
-        tsf = self.tsf_model._stream(tsf_inputs, False, 'inference')
-        tsf.load_input(tsf_inputs.float())
+        if (pred_hwc is not None or pred_u8 is not None) and bg is None:
+            raise LwbError("pred_hwc / pred_u8 need bg (they hold the composite)")
+        tsf_inputs = tsf_inputs.float().contiguous()
         T = T.float().contiguous()
-        tsf.encode(warp_srcs=[None] + [_nhwc_of(a) for a in src_encoder_outs[1:]], T=T, ac=ac)
-        tsf.resnets(warp_srcs=[_nhwc_of(a) for a in src_resnet_outs], T=T, ac=ac)
-        tsf.decode()
-        if pred_hwc is not None or pred_u8 is not None:
-            if bg is None:
-                raise LwbError("pred_hwc / pred_u8 need bg (they hold the composite)")
-            color, mask, pred = tsf.heads(bg, pred_hwc=pred_hwc, pred_u8=pred_u8)
+        enc_w = [None] + [_nhwc_of(a) for a in src_encoder_outs[1:]]
+        res_w = [_nhwc_of(a) for a in src_resnet_outs]
+        B = tsf_inputs.shape[0]
+        nsub = _sub_batches(B, enc_w, res_w, bg)
+
+        def run(tag, x, Tx, outs):
+            tsf = self.tsf_model._stream(x, False, tag)
+            tsf.load_input(x)
+            tsf.encode(warp_srcs=enc_w, T=Tx, ac=ac)
+            tsf.resnets(warp_srcs=res_w, T=Tx, ac=ac)
+            tsf.decode()
+            return tsf.heads(bg, **outs)
+
+        if nsub == 1:
+            outs = {}
+            if pred_hwc is not None or pred_u8 is not None:
+                outs = dict(pred_hwc=pred_hwc, pred_u8=pred_u8)
+            color, mask, pred = run('inference', tsf_inputs, T, outs)
         else:
-            color, mask, pred = tsf.heads(bg)
+            # LWB_STREAMS sub-batches on side streams: the HBM-bound kernels of one sub-batch (InstanceNorm / warp, heads
+            # composite, input packing) co-run with the tensor-bound convolutions of the other, and the second wave of
+            # the twelve 512-channel layers (128 tile pairs on 74 SM pairs) is filled by the other sub-batch's tiles.
+            _, _, H, W = tsf_inputs.shape
+            dev = tsf_inputs.device
+            color = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+            mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+            pred = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev) if bg is not None else None
+            side = self.__dict__.setdefault('_lwb_side_streams', {})
+            cur = torch.cuda.current_stream(dev)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            step = B // nsub
+            for i in range(nsub):
+                if (dev, i) not in side:
+                    side[(dev, i)] = torch.cuda.Stream(device=dev)
+                st = side[(dev, i)]
+                st.wait_event(ready)
+                a, b = i * step, (i + 1) * step
+                with torch.cuda.stream(st):
+                    outs = dict(color=color[a:b], mask=mask[a:b])
+                    if pred is not None:
+                        outs['pred'] = pred[a:b]
+                    if pred_hwc is not None:
+                        outs['pred_hwc'] = pred_hwc[a:b]
+                    if pred_u8 is not None:
+                        outs['pred_u8'] = pred_u8[a:b]
+                    run('inference#%d' % i, tsf_inputs[a:b], T[a:b], outs)
+                    done = torch.cuda.Event()
+                    done.record(st)
+                cur.wait_event(done)
         if bg is not None:
             return color, mask, pred
         return color, mask

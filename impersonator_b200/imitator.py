@@ -16,9 +16,10 @@ processed ``opt.batch_size`` at a time -- one fused correspondence pass (raster 
 warp), one generator pass on the tcgen05 conv engine, one device->host copy per chunk -- and the
 results are returned per frame, in order, with ``tsf_info`` describing the last frame.
 
-Out of scope: HMR / SMPL (``networks/hmr.py``; need external model files) --
-any object with ``__call__(img) -> theta`` and ``get_details(theta) -> {cam, pose, shape, verts, ...}``
-can be injected as ``hmr``; ``post_personalize`` (fine-tuning, needs backward); Mask-RCNN detector.
+``tgt_smpls=None`` (how run_imitator.py:239-241 calls it) sends the target images through the HMR encoder
+(impersonator_b200.hmr, one batch per chunk).  Out of scope: ``post_personalize`` (fine-tuning,
+needs backward) and the Mask-RCNN detector.  Any object with ``__call__(img) -> theta`` and ``get_details(theta)``
+can be injected as ``hmr`` (tests use a synthetic body model).
 """
 import os
 
@@ -64,46 +65,107 @@ def _save_image(img, path, image_size=None, normalize=False):
 
 
 class Imitator(object):
+    """``Imitator(opt)`` builds everything from ``opt`` exactly like models/imitator.py:15-74 (+ models/models.py:64-76,
+    159-179): generator through ``NetworksFactory`` + checkpoint, background net, HMR (+ SMPL), ``SMPLRenderer`` from the
+    asset files.  The keyword arguments are an extension: any of them replaces the corresponding constructed object
+    (tests and benchmarks inject synthetic networks / tables because every asset is an external download)."""
+
     def __init__(self, opt, generator=None, bgnet=None, hmr=None, render=None, device=None):
         self._name = 'Imitator'
         self._opt = opt
+        self._gpu_ids = getattr(opt, 'gpu_ids', '0')
+        self._is_train = getattr(opt, 'is_train', False)
+        self._save_dir = os.path.join(getattr(opt, 'checkpoints_dir', './outputs/checkpoints/'), getattr(opt, 'name', 'running'))
         self.device = torch.device(device if device is not None else 'cuda')
-        self._G_cond_nc = getattr(opt, 'cond_nc', 3)
-        self.generator = (generator if generator is not None else self._create_generator()).to(self.device).eval()
-        bg_model = getattr(opt, 'bg_model', 'ORIGINAL')
-        if bgnet is not None:
-            self.bgnet = bgnet.to(self.device).eval()
-        elif bg_model == 'ORIGINAL':
-            self.bgnet = self.generator.bg_model
-        else:
-            from .inpaintor import InpaintSANet
-            self.bgnet = InpaintSANet(c_dim=4)
-            self._load_params(self.bgnet, bg_model)
-            self.bgnet = self.bgnet.to(self.device).eval()
-        self.hmr = hmr
-        if render is None:
-            raise LwbError("pass render=SMPLRenderer(...) (the SMPL face/uv assets are external downloads)")
-        self.render = render.to(self.device)
-        self.detector = None
+        self._G_cond_nc, self._D_cond_nc = self.cond_nc()
+        self._create_networks(generator, bgnet, hmr, render)
         self.src_info = None
         self.tsf_info = None
         self.first_cam = None
 
-    # ---- construction helpers (models/imitator.py:54-67, models/models.py:159-179) -------------
-    def _create_generator(self):
-        net = ImpersonatorGenerator(bg_dim=4, src_dim=3 + self._G_cond_nc, tsf_dim=3 + self._G_cond_nc,
-                                    repeat_num=getattr(self._opt, 'repeat_num', 6))
-        path = getattr(self._opt, 'load_path', '')
-        if path:
-            self._load_params(net, path)
+    @property
+    def name(self):
+        return self._name
+
+    def cond_nc(self):
+        """models/models.py:85-95."""
+        map_name = getattr(self._opt, 'map_name', '')
+        if map_name:
+            from .mesh import get_map_fn_dim
+            nc = get_map_fn_dim(map_name)
+            return nc, nc
+        nc = getattr(self._opt, 'cond_nc', 3)
+        return nc, nc
+
+    # ---- construction (models/imitator.py:25-74) -------------------------------------------------
+    def _create_networks(self, generator=None, bgnet=None, hmr=None, render=None):
+        opt = self._opt
+        self.generator = (generator if generator is not None else self._create_generator()).to(self.device).eval()
+        if bgnet is not None:
+            self.bgnet = bgnet.to(self.device).eval()
+        elif getattr(opt, 'bg_model', 'ORIGINAL') != 'ORIGINAL':
+            self.bgnet = self._create_bgnet().to(self.device).eval()
+        else:
+            self.bgnet = self.generator.bg_model
+        if hmr is not None:
+            self.hmr = hmr.to(self.device) if hasattr(hmr, 'to') else hmr
+        else:
+            self.hmr = self._create_hmr().to(self.device).eval()
+        if render is None:
+            render = SMPLRenderer(image_size=opt.image_size, tex_size=getattr(opt, 'tex_size', 3),
+                                  has_front=getattr(opt, 'front_warp', False), fill_back=False)
+        self.render = render.to(self.device)
+        if getattr(opt, 'has_detector', False):
+            raise LwbError("has_detector: the Mask-RCNN person detector (utils/detectors.py) is outside the hot path "
+                           "(SURVEY.md section 8); the silhouette-based masks of models/imitator.py:123-125 are used")
+        self.detector = None
+
+    def _create_bgnet(self):
+        from .networks import NetworksFactory
+        net = NetworksFactory.get_by_name('deepfillv2', c_dim=4)
+        self._load_params(net, self._opt.bg_model, need_module=False)
+        net.eval()
         return net
 
+    def _create_generator(self):
+        from .networks import NetworksFactory
+        opt = self._opt
+        net = NetworksFactory.get_by_name(getattr(opt, 'gen_name', 'impersonator'), bg_dim=4, src_dim=3 + self._G_cond_nc,
+                                          tsf_dim=3 + self._G_cond_nc, repeat_num=getattr(opt, 'repeat_num', 6))
+        load_path, load_epoch = getattr(opt, 'load_path', ''), getattr(opt, 'load_epoch', -1)
+        if load_path:
+            self._load_params(net, load_path)
+        elif load_epoch > 0:
+            self._load_network(net, 'G', load_epoch)
+        else:
+            raise ValueError('load_path {} is empty and load_epoch {} is 0'.format(load_path, load_epoch))
+        net.eval()
+        return net
+
+    def _create_hmr(self):
+        from .networks import HumanModelRecovery
+        hmr = HumanModelRecovery(self._opt.smpl_model)
+        saved_data = torch.load(self._opt.hmr_model, map_location='cpu')
+        hmr.load_state_dict(saved_data)
+        hmr.eval()
+        return hmr
+
+    def _load_network(self, network, network_label, epoch_label, need_module=False):
+        """models/models.py:153-157."""
+        load_path = os.path.join(self._save_dir, 'net_epoch_%s_id_%s.pth' % (epoch_label, network_label))
+        self._load_params(network, load_path, need_module)
+
     @staticmethod
-    def _load_params(net, path, need_module=False):
-        sd = torch.load(path, map_location='cpu')
-        if not need_module:
-            sd = {(k[7:] if k.startswith('module.') else k): v for k, v in sd.items()}
-        net.load_state_dict(sd)
+    def _load_params(network, load_path, need_module=False):
+        """models/models.py:159-179."""
+        assert os.path.exists(load_path), \
+            'Weights file not found. Have you trained a model!? We are not providing one %s' % load_path
+        save_data = torch.load(load_path, map_location='cpu')
+        if need_module:
+            network.load_state_dict(save_data)
+        else:
+            network.load_state_dict({(k[7:] if 'module' in k else k): v for k, v in save_data.items()})
+        print('Loading net: %s' % load_path)
 
     @property
     def _ac(self):
@@ -256,14 +318,25 @@ class Imitator(object):
         With ``output_dir`` the uint8 images come from the GPU and go straight to cv2.imwrite."""
         length = len(tgt_paths)
         outputs = []
-        if tgt_smpls is None:
-            # frames come through HMR one by one (reference behaviour); still one sync per frame only
-            for t in range(length):
-                tsf_inputs = self.transfer_params(tgt_paths[t], None, cam_strategy, t=t)
-                preds = self.forward(tsf_inputs, self.tsf_info['T'])
-                outputs.append(preds[0].permute(1, 2, 0).cpu().numpy())
-                self._maybe_save(outputs[-1], tgt_paths[t], output_dir, t)
-            return outputs
+        last_image = [None]
+        originals = {}                                           # frame index -> original RGB image (for the gt_ files)
+
+        def chunk_smpls(a, b):
+            """SMPL vectors of frames a..b-1: given, or estimated from the target images by HMR -- one encoder batch per
+            chunk instead of one launch sequence per frame (models/imitator.py:271-275)."""
+            if tgt_smpls is not None:
+                return torch.as_tensor(np.stack([np.asarray(s, dtype=np.float32).reshape(-1) for s in tgt_smpls[a:b]]))
+            if self.hmr is None or not callable(self.hmr):
+                raise LwbError("tgt_smpls required when no HMR network is available")
+            import cv2
+            batch = []
+            for k, path in enumerate(tgt_paths[a:b]):
+                _, ori = _read_image(path, self._opt.image_size)
+                batch.append(cv2.resize(ori, (224, 224)).astype(np.float32).transpose((2, 0, 1)) / 255.0 * 2 - 1.0)
+                last_image[0] = ori
+                if output_dir:
+                    originals[a + k] = ori
+            return self.hmr(torch.from_numpy(np.stack(batch)).to(self.device))
         # Chunks are pipelined: the D2H of chunk i runs on a copy stream while chunk i+1 computes; the host only
         # waits for a chunk's copy when it has already queued the next chunk (and once at the end).
         main = torch.cuda.current_stream(self.device)
@@ -282,10 +355,11 @@ class Imitator(object):
                 for j in range(b0 - a0):
                     outputs.append(host[j])
                     if output_dir:
-                        self._maybe_save(h_u8[j], tgt_paths[a0 + j], output_dir, a0 + j, is_bgr_u8=True)
+                        self._maybe_save(h_u8[j], tgt_paths[a0 + j], output_dir, a0 + j, is_bgr_u8=True,
+                                         original=originals.pop(a0 + j, None))
 
         for (a, b) in self._chunks(length):
-            smpls = torch.as_tensor(np.stack([np.asarray(s, dtype=np.float32) for s in tgt_smpls[a:b]]))
+            smpls = chunk_smpls(a, b)
             tsf_inputs = self.transfer_params_by_smpl(smpls, cam_strategy, t=a)
             want_u8 = bool(as_uint8 or output_dir)
             preds = self.forward(tsf_inputs, self.tsf_info['T'], host_layout=dict(hwc=not as_uint8, u8=want_u8))
@@ -309,6 +383,8 @@ class Imitator(object):
             drain(keep=1)
         drain(keep=0)
         self._last_frame_info()
+        if last_image[0] is not None:
+            self.tsf_info['image'] = last_image[0]
         if range_bits[0] and not getattr(self, '_range_retry', False):
             # Never silently: activations left the range in which the default fp16f8 operand split keeps its precision
             # (|x| >= 1024: the e4m3 correction terms clip).  Pin the generator to fp16x3 (fp16 corrections, range 6e4)
@@ -351,11 +427,17 @@ class Imitator(object):
             if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] > 1:
                 info[k] = v[-1:]
 
-    def _maybe_save(self, pred, tgt_path, output_dir, t, is_bgr_u8=False):
+    def _maybe_save(self, pred, tgt_path, output_dir, t, is_bgr_u8=False, original=None):
+        """pred_<file> (+ gt_<file> = the driving frame resized, models/imitator.py:182-187); inference_by_smpls names
+        its frames pred_%.8d.jpg (:212)."""
         if not output_dir:
             return
         name = os.path.split(tgt_path)[-1] if tgt_path else 'pred_%.8d.jpg' % t
         path = os.path.join(output_dir, 'pred_' + name if tgt_path else name)
+        if tgt_path:
+            if original is None:
+                _, original = _read_image(tgt_path, self._opt.image_size)
+            _save_image(original, os.path.join(output_dir, 'gt_' + name), image_size=self._opt.image_size)
         if is_bgr_u8:
             import cv2
             cv2.imwrite(path, pred)                      # already what save_cv2_img(normalize=True) would write

@@ -6,10 +6,15 @@ stats): ``GatedConv2dWithActivation`` (conv2d, mask_conv2d, batch_norm2d), ``Gat
 (nearest 2x + gated conv), ``SelfAttention`` (query/key/value 1x1 convs, gamma), ``InpaintSANet``
 (coarse_net 17 / refine_conv_net 11 / refine_attn / refine_upsample_net 7).
 
-Execution: every gated layer = ONE direct-conv launch computing both convs (weights stacked on the
-output channels) + one fused gate/BatchNorm kernel (lwb_conv2d_direct_nchw, lwb_gated_bn_nchw).
-This path runs once per source image, off the per-frame loop; the 4096x4096 self-attention uses the
-library batched GEMM (torch.bmm -> cuBLAS) + softmax, as a plain library call.
+Execution (``InpaintSANet.forward``): the whole network is bound once per input shape to persistent NHWC
+buffers (``_InpaintStream``).  Every gated layer = ONE tcgen05 conv-engine plan over the stacked
+[conv2d ; mask_conv2d] filters (bias, dilation 2-16, 5x5, 4x4 stride 2; channels zero-padded to the engine's
+64-wide K chunks / 16-wide N) + the fused gate / BatchNorm / nearest-2x / clamp epilogue
+(lwb_gated_act_nhwc) that emits the next layer's operands directly; the 4096 x 4096 self-attention is the
+stacked 1x1 q/k/v convolution on the engine + a flash-style fp32 kernel (lwb_self_attention_nhwc).  No
+library GEMM / softmax is left on this path.  It runs once per source image, off the per-frame loop.
+The sub-modules stay callable on their own (``GatedConv2dWithActivation.forward`` etc.: the fp32 direct
+convolution + lwb_gated_bn_nchw), which is what unit tests of single layers use.
 """
 import numpy as np
 import torch
@@ -162,19 +167,170 @@ class InpaintSANet(torch.nn.Module):
             G(cnum, cnum // 2, 3, 1, padding=get_pad(256, 3, 1)),
             G(cnum // 2, 3, 3, 1, padding=get_pad(256, 3, 1), activation=None))
 
+    def _invalidate(self):
+        self.__dict__['_lwb_streams'] = {}
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super(InpaintSANet, self).load_state_dict(*args, **kwargs)
+        self._invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super(InpaintSANet, self)._apply(fn, *args, **kwargs)
+        self._invalidate()
+        return out
+
+    def _stream(self, x):
+        from .generator import _split_mode
+        B, _, H, W = x.shape
+        split = _split_mode(self)
+        streams = self.__dict__.setdefault('_lwb_streams', {})
+        key = (B, H, W, split)
+        if key not in streams:
+            while len(streams) >= 2:
+                streams.pop(next(iter(streams)))
+            streams[key] = _InpaintStream(self, B, H, W, x.device, split)
+        return streams[key]
+
     @torch.no_grad()
     def forward(self, imgs, masks, only_out=False, only_x=False):
+        if self.training:
+            raise LwbError("the B200 path is inference-only (eval-mode BatchNorm)")
+        if not imgs.is_cuda:
+            raise LwbError("InpaintSANet runs on CUDA tensors only (no CPU fallback)")
+        imgs, masks = imgs.float(), masks.float()
+        st = self._stream(imgs)
         masked_imgs = imgs * (1 - masks) + masks
-        x = self.coarse_net(torch.cat([masked_imgs, masks], dim=1))
-        coarse_x = torch.clamp(x, -1., 1.)
+        coarse_x = st.run_coarse(torch.cat([masked_imgs, masks], dim=1))          # clamp fused into the last epilogue (:187)
         masked_imgs = imgs * (1 - masks) + coarse_x * masks
-        x = self.refine_conv_net(torch.cat([masked_imgs, masks], dim=1))
-        x = self.refine_attn(x)
-        x = self.refine_upsample_net(x)
-        x = torch.clamp(x, -1., 1.)
+        x = st.run_refine(torch.cat([masked_imgs, masks], dim=1))                 # conv net + attention + upsample net, clamped (:196)
         comp_imgs = x * masks + imgs * (1 - masks)
         if only_out:
             return comp_imgs
         if only_x:
             return x
         return coarse_x, x, comp_imgs
+
+
+def _ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+class _InpaintStream(object):
+    """InpaintSANet bound to (batch, H, W, precision): NHWC operand buffers, conv plans over the stacked gated filters,
+    folded BatchNorms.  Channel counts (4, 16, 32) below the engine's 64-wide K chunk are zero-padded."""
+
+    def __init__(self, net, B, H, W, dev, split):
+        from .generator import _Act
+        if H % 4 or W % 4:
+            raise LwbError("InpaintSANet needs H, W divisible by 4")
+        self.B, self.H, self.W, self.dev, self.split = B, H, W, dev, split
+        self.lo_format = 1 if split == 2 else 0
+        self.range_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._pend = []
+        self._Act = _Act
+        self.in_f32 = torch.zeros((B, H, W, 64), dtype=torch.float32, device=dev)         # channels 4..63 stay zero
+        self.x_in = _Act((B, H, W, 64), dev, split)
+        self.coarse, h, w = self._chain(list(net.coarse_net), self.x_in, H, W, final_f32=True)
+        self.refine, h, w = self._chain(list(net.refine_conv_net), self.x_in, H, W, keep_last_f32=True)
+        # self attention on [B, h, w, 128]: stacked 1x1 q / k / v convolution (16 + 16 + 128 = 160 output channels)
+        att = net.refine_attn
+        c = att.chanel_in
+        if c != 128:
+            raise LwbError("the attention kernel is specialised for SelfAttention(128)")
+        wq = torch.cat([att.query_conv.weight, att.key_conv.weight, att.value_conv.weight], dim=0).detach().float()
+        self.att_bias = torch.cat([att.query_conv.bias, att.key_conv.bias, att.value_conv.bias]).detach().float().contiguous()
+        self.att_gamma = att.gamma.detach().float().contiguous()
+        last = self.refine[-1]
+        self.att_x = last["y_f32"]
+        self.att_raw = torch.empty((B, h, w, wq.shape[0]), dtype=torch.float32, device=dev)
+        d = K.make_conv_desc(B, h, w, 128, wq.shape[0], 1, 1, pad=0, split=split)
+        self.att_rec = dict(desc=d, x=last["out"].pair, w=wq, cout_pad=wq.shape[0], cin_pad=128, raw=self.att_raw)
+        self._pend.append(self.att_rec)
+        self.att_out = torch.empty((B, h, w, 128), dtype=torch.float32, device=dev)
+        self.att_act = _Act((B, h, w, 128), dev, split)
+        self.upsample, h, w = self._chain(list(net.refine_upsample_net), self.att_act, h, w, final_f32=True)
+        # one max|w| sync for the whole network, then pack + plan
+        amax = [None] * len(self._pend)
+        if split == 2:
+            amax = torch.stack([p["w"].abs().max().float() for p in self._pend]).tolist()
+        for p, a in zip(self._pend, amax):
+            wp = K.pack_conv_weight(p["w"], cout_pad=p["cout_pad"], cin_pad=p["cin_pad"], split=split, absmax=a)
+            p["plan"] = K.ConvPlan(p["desc"], p["x"], None, wp, p["raw"], None)
+        del self._pend
+
+    def _chain(self, layers, x_act, h, w, final_f32=False, keep_last_f32=False):
+        """Bind a Sequential of gated (de)conv layers.  -> (records, h, w) of the output."""
+        B, dev, split = self.B, self.dev, self.split
+        recs = []
+        up_next = 1
+        for i, m in enumerate(layers):
+            is_de = isinstance(m, GatedDeConv2dWithActivation)
+            g = m.conv2d if is_de else m
+            conv = g.conv2d
+            cout, cin, k, _ = conv.weight.shape
+            stride, pad, dil = conv.stride[0], conv.padding[0], conv.dilation[0]
+            cin_pad = x_act.hi.shape[3]
+            wst = torch.cat([conv.weight, g.mask_conv2d.weight], dim=0).detach().float()
+            cout_pad = _ceil_to(2 * cout, 16)
+            d = K.make_conv_desc(B, h, w, cin_pad, cout_pad, k, k, stride=stride, pad=pad, dil=dil, split=split)
+            raw = torch.empty((B, d.h_out, d.w_out, cout_pad), dtype=torch.float32, device=dev)
+            rec = dict(desc=d, x=x_act.pair, w=wst, cout_pad=cout_pad, cin_pad=cin_pad, raw=raw, c=cout)
+            rec["bias"] = torch.cat([conv.bias, g.mask_conv2d.bias]).detach().float().contiguous() if conv.bias is not None else None
+            rec["act"] = 0 if g.activation is None else 2
+            if g.batch_norm:
+                bn = g.batch_norm2d
+                sc = (bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps))
+                rec["scale"] = sc.float().contiguous()
+                rec["shift"] = (bn.bias.detach().double() - bn.running_mean.detach().double() * sc).float().contiguous()
+            else:
+                rec["scale"] = rec["shift"] = None
+            h, w = d.h_out, d.w_out
+            last = (i == len(layers) - 1)
+            # a GatedDeConv that FOLLOWS consumes this layer's output on the 2x nearest grid (networks/inpaintor.py:67)
+            nxt_de = (not last) and isinstance(layers[i + 1], GatedDeConv2dWithActivation)
+            rec["up"] = 2 if nxt_de else 1
+            if last and final_f32:
+                rec["out"], rec["y_f32"], rec["clamp"] = None, torch.empty((B, h, w, cout), dtype=torch.float32, device=dev), True
+            else:
+                rec["out"] = self._Act((B, h * rec["up"], w * rec["up"], _ceil_to(cout, 64)), dev, split)
+                rec["y_f32"] = torch.empty((B, h, w, cout), dtype=torch.float32, device=dev) if (last and keep_last_f32) else None
+                rec["clamp"] = False
+                x_act = rec["out"]
+                h, w = h * rec["up"], w * rec["up"]
+            self._pend.append(rec)
+            recs.append(rec)
+        return recs, h, w
+
+    def _load(self, x):
+        """NCHW fp32 [B,4,H,W] -> the shared 64-channel operand buffer (channels 4.. are zero)."""
+        if tuple(x.shape) != (self.B, 4, self.H, self.W):
+            raise LwbError("unexpected inpaintor input %s" % (tuple(x.shape),))
+        self.in_f32[..., :4].copy_(x.permute(0, 2, 3, 1))
+        K.norm_act_nhwc(self.in_f32, None, None, None, False, None, y_hi=self.x_in.hi, y_lo=self.x_in.lo,
+                        lo_format=self.lo_format, range_flag=self.range_flag)
+
+    def _run_chain(self, recs):
+        for r in recs:
+            r["plan"].run()
+            out = r["out"]
+            K.gated_act_nhwc(r["raw"], r["c"], r["bias"], r["act"], r["scale"], r["shift"], upsample=r["up"], clamp=r["clamp"],
+                             y_f32=r["y_f32"], y_hi=out.hi if out is not None else None, y_lo=out.lo if out is not None else None,
+                             lo_format=self.lo_format, range_flag=self.range_flag)
+        return recs[-1]
+
+    def run_coarse(self, x):
+        self.range_flag.zero_()
+        self._load(x)
+        last = self._run_chain(self.coarse)
+        return K.nhwc_to_nchw(last["y_f32"])
+
+    def run_refine(self, x):
+        self._load(x)
+        self._run_chain(self.refine)
+        self.att_rec["plan"].run()
+        K.self_attention_nhwc(self.att_raw, self.att_bias, self.att_x, self.att_gamma, out=self.att_out)
+        K.norm_act_nhwc(self.att_out, None, None, None, False, None, y_hi=self.att_act.hi, y_lo=self.att_act.lo,
+                        lo_format=self.lo_format, range_flag=self.range_flag)
+        last = self._run_chain(self.upsample)
+        return K.nhwc_to_nchw(last["y_f32"])

@@ -421,6 +421,81 @@ def conv2d_direct_nchw(x, w, bias=None, stride=1, pad=0, dil=1):
     return out
 
 
+def gated_act_nhwc(raw, c, bias, act, scale, shift, upsample=1, clamp=False, y_f32=None, y_hi=None, y_lo=None,
+                   lo_format=0, range_flag=None):
+    """Gated-conv epilogue on the conv engine's raw NHWC output [n,h,w,c_stride >= 2c] (lwb_gated_act_nhwc):
+    y = BN(act(a + bias_a) * sigmoid(b + bias_b)) -> optional fp32 [n,h*u,w*u,*] and the next layer's operands
+    [n,h*u,w*u,c_pad] (zero-padded channels), on the 2x nearest-neighbour grid when upsample = 2."""
+    _chk_cuda(raw, bias, scale, shift, y_f32, y_hi, y_lo, range_flag)
+    n, h, w, cs = raw.shape
+    u = int(upsample)
+    for t in (y_f32, y_hi):
+        if t is not None and tuple(t.shape[:3]) != (n, h * u, w * u):
+            raise LwbError("gated_act: output grid must be [n, %d, %d, *]" % (h * u, w * u))
+    _count(1)
+    check(lib().lwb_gated_act_nhwc(ptr(raw), n, h, w, int(c), cs, ptr(bias), int(act), ptr(scale), ptr(shift), u, 1 if clamp else 0,
+                                   ptr(y_f32), y_f32.shape[3] if y_f32 is not None else 0, ptr(y_hi), ptr(y_lo),
+                                   y_hi.shape[3] if y_hi is not None else 0, int(lo_format), ptr(range_flag), stream()),
+          "lwb_gated_act_nhwc")
+
+
+def self_attention_nhwc(qkv, bias, x, gamma, dq=16, out=None):
+    """SelfAttention (networks/inpaintor.py:86-107): qkv [n,h,w,ld] = [q | k | v | pad] raw 1x1-conv output, bias
+    [2*dq+dv], x [n,h,w,dv] fp32 -> gamma * softmax(q k^T) v + x."""
+    _chk_cuda(qkv, bias, x, gamma, out)
+    n, h, w, ld = qkv.shape
+    dv = x.shape[3]
+    if out is None:
+        out = torch.empty_like(x)
+    _count(1)
+    check(lib().lwb_self_attention_nhwc(ptr(qkv), ld, ptr(bias), n, h * w, int(dq), dv, ptr(x), ptr(gamma), ptr(out), stream()),
+          "lwb_self_attention_nhwc")
+    return out
+
+
+def maxpool_nchw_to_nhwc(x, k, stride, out=None):
+    """F.max_pool2d(x, k, stride, ceil_mode=True) (networks/hmr.py:150): NCHW fp32 -> NHWC fp32."""
+    _chk_cuda(x, out)
+    n, c, h, w = x.shape
+    ho, wo = -(-(h - k) // stride) + 1, -(-(w - k) // stride) + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device)
+    _count(1)
+    check(lib().lwb_maxpool_nchw_to_nhwc(ptr(x), n, c, h, w, k, stride, ptr(out), stream()), "lwb_maxpool_nchw_to_nhwc")
+    return out
+
+
+def global_avgpool_nhwc(x, scale=None, shift=None, relu=False, out=None, ld_out=None):
+    """mean over pixels of relu?(x*scale+shift): x NHWC fp32 [n,h,w,c] -> out [n, ld_out] (first c columns)."""
+    _chk_cuda(x, scale, shift)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    ld = ld_out if ld_out is not None else out.stride(0)
+    _count(1)
+    check(lib().lwb_global_avgpool_nhwc(ptr(x), n, h * w, c, ptr(scale), ptr(shift), 1 if relu else 0, ptr(out), ld, stream()),
+          "lwb_global_avgpool_nhwc")
+    return out
+
+
+def linear(x, w, bias=None, relu=False, out=None, accumulate=False):
+    """nn.Linear (+ReLU): x [n,k] (row stride x.stride(0)), w [m,k] -> out [n,m] (row stride out.stride(0)), += if accumulate."""
+    _chk_cuda(w, bias)
+    for t in (x, out):
+        if t is not None and (not t.is_cuda or t.stride(-1) != 1):
+            raise LwbError("linear expects CUDA tensors with unit inner stride")
+    n, k = x.shape
+    m = w.shape[0]
+    if w.shape[1] != k:
+        raise LwbError("linear: weight is [%d,%d], input has %d features" % (m, w.shape[1], k))
+    if out is None:
+        out = torch.empty((n, m), dtype=torch.float32, device=x.device)
+    _count(1)
+    check(lib().lwb_linear(ptr(x), x.stride(0), ptr(w), ptr(bias), n, k, m, 1 if relu else 0, 1 if accumulate else 0,
+                           ptr(out), out.stride(0), stream()), "lwb_linear")
+    return out
+
+
 def gated_bn_nchw(ab, act, scale=None, shift=None):
     """networks/inpaintor.py:37-47: act(a)*sigmoid(b) followed by folded eval-mode BatchNorm."""
     _chk_cuda(ab, scale, shift)

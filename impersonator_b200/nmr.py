@@ -12,9 +12,10 @@ the per-frame work runs in the fused sm_100a correspondence kernels (lwb_corresp
   correspond(cam, vertices, src_p2verts, src_img)  [new]  everything transfer_params_by_smpl needs
                                                            (models/imitator.py:251-260) in one pass
 
-The SMPL assets (``smpl_faces.npy``, ``mapper.txt``) are external downloads in the reference
-(README.md:48-68); when they are absent the tables can be passed in directly
-(``faces=``, ``map_fn=``, ...), which is how the synthetic benchmarks run.
+Construction follows utils/nmr.py:104-178: ``smpl_faces.npy`` + the lookup tables built from ``mapper.txt`` /
+``front_facial.json`` / ``head.json`` by impersonator_b200.mesh (utils/mesh.py:368-421).  Those assets are external
+downloads in the reference (README.md:48-68); the tables can also be passed in directly (``faces=``, ``map_fn=``,
+...), which is how the synthetic benchmarks run.
 Textured / lit rendering (``render``, ``extract_tex``, ...) is visualisation only: out of scope.
 """
 import os
@@ -49,28 +50,40 @@ class SMPLRenderer(nn.Module):
         self.fill_back = fill_back
         self.map_name = map_name
         self.tex_size = tex_size
-        if faces is None:
-            if not os.path.exists(face_path):
-                raise LwbError("%s not found: pass faces= / map_fn= tables explicitly (the SMPL assets are an "
-                               "external download, README.md:48-68)" % face_path)
+        from_files = faces is None
+        if from_files:
+            # the reference's own construction path (utils/nmr.py:137-161): tables from the asset files
+            if not os.path.exists(face_path) or not os.path.exists(uv_map_path):
+                raise LwbError("%s / %s not found: the SMPL assets are an external download (README.md:48-68); "
+                               "or pass faces= / map_fn= tables explicitly" % (face_path, uv_map_path))
             faces = np.load(face_path)
-        faces = torch.as_tensor(np.asarray(faces)).int()
+        faces = torch.as_tensor(np.asarray(faces).astype(np.int32)).int()
         self.base_nf = faces.shape[0]
         if self.fill_back:
             faces = torch.cat((faces, faces.flip(1)), dim=0)
         self.nf = faces.shape[0]
         self.register_buffer('faces', faces.contiguous())
+        if from_files:
+            from . import mesh
+            if map_fn is None:
+                map_fn = mesh.create_mapping(map_name, uv_map_path, contain_bg=True, fill_back=fill_back)
+            if back_map_fn is None:
+                back_map_fn = mesh.create_mapping('back', uv_map_path, contain_bg=True, fill_back=fill_back)
+            if has_front and front_map_fn is None:
+                front_map_fn = mesh.create_mapping('front', uv_map_path, contain_bg=True, fill_back=fill_back)
         if map_fn is None:
-            raise LwbError("map_fn table required (utils/mesh.py:create_mapping needs mapper.txt, an external asset)")
-        self.register_buffer('map_fn', torch.as_tensor(map_fn).float().contiguous())
+            raise LwbError("map_fn table required when faces= is given explicitly")
+        if np.asarray(map_fn).shape[0] != self.nf + 1:
+            raise LwbError("map_fn has %d rows, the mesh %d faces (+1 background row)" % (np.asarray(map_fn).shape[0], self.nf))
+        self.register_buffer('map_fn', torch.as_tensor(np.asarray(map_fn)).float().contiguous())
         if back_map_fn is not None:
-            self.register_buffer('back_map_fn', torch.as_tensor(back_map_fn).float().contiguous())
+            self.register_buffer('back_map_fn', torch.as_tensor(np.asarray(back_map_fn)).float().contiguous())
         else:
             self.back_map_fn = None
         if has_front:
             if front_map_fn is None:
                 raise LwbError("has_front=True needs front_map_fn")
-            self.register_buffer('front_map_fn', torch.as_tensor(front_map_fn).float().contiguous())
+            self.register_buffer('front_map_fn', torch.as_tensor(np.asarray(front_map_fn)).float().contiguous())
         else:
             self.front_map_fn = None
         self.rasterizer_eps = 1e-3

@@ -53,7 +53,10 @@ class SMPL(nn.Module):
         batch_smpl.py:318-321 is linear in beta, so J = J0 + JS beta with J0 = J_regressor^T v_template and
         JS = J_regressor^T shapedirs folded here (float64, once)."""
         dev = self.v_template.device
-        if self._dm is not None and self._dm["v_template"].device == dev and self._dm["_src"] is self.v_template:
+        bufs = (self.v_template, self.shapedirs, self.J_regressor, self.posedirs, self.weights, self.joint_regressor)
+        # keyed on identity AND in-place version of every buffer: load_state_dict copies into the same tensor objects
+        stamp = tuple((id(b), b._version) for b in bufs)
+        if self._dm is not None and self._dm["v_template"].device == dev and self._dm["_stamp"] == stamp:
             return self._dm
         V = self.size[0]
         Jr = self.J_regressor.double().t()                                       # [24, V]
@@ -64,7 +67,7 @@ class SMPL(nn.Module):
                         posedirs=self.posedirs.contiguous(), weights=self.weights.contiguous(),
                         j_template=j_template, j_shapedirs=j_shapedirs,
                         parents=torch.as_tensor(self.parents.astype(np.int32), device=dev),
-                        joint_regressor_t=self.joint_regressor.t().contiguous(), _src=self.v_template)
+                        joint_regressor_t=self.joint_regressor.t().contiguous(), _stamp=stamp)
         return self._dm
 
     def forward(self, beta, theta, get_skin=False, cam=None):

@@ -112,7 +112,8 @@ def _key_gen(seed, key):
 def fill_state_dict(template, seed=0, conv_std=0.02):
     """Deterministic weights for a ``state_dict``-shaped template (key -> tensor or shape).
 
-    Values depend only on (seed, key, shape): >=2-D tensors ~ N(0, conv_std); 1-D ``*.weight``
+    Values depend only on (seed, key, shape): >=2-D tensors ~ N(0, conv_std) (``conv_std='he'``: N(0, 2 / fan_in),
+    which keeps activations O(1) through BatchNorm-in-eval networks such as the HMR encoder); 1-D ``*.weight``
     ~ 1 + 0.1 N(0,1) (norm scales); 1-D ``*.bias`` ~ 0.1 N(0,1); ``running_var`` ~ U(0.5, 1.5);
     ``running_mean`` ~ 0.1 N(0,1); integer buffers (``num_batches_tracked``) = 0.
     """
@@ -124,7 +125,13 @@ def fill_state_dict(template, seed=0, conv_std=0.02):
         if not dtype.is_floating_point:
             out[key] = torch.zeros(shape, dtype=dtype)
         elif len(shape) >= 2:
-            out[key] = torch.randn(shape, generator=g) * conv_std
+            std = conv_std
+            if conv_std == 'he':
+                fan_in = 1
+                for d in shape[1:]:
+                    fan_in *= d
+                std = math.sqrt(2.0 / fan_in)
+            out[key] = torch.randn(shape, generator=g) * std
         elif key.endswith('running_var'):
             out[key] = 0.5 + torch.rand(shape, generator=g)
         elif key.endswith('running_mean'):
@@ -232,3 +239,95 @@ def synthetic_smpl_params(batch, seed=17):
                                 torch.randn(batch, generator=g) * 0.1], dim=1)
     shape = torch.randn(batch, 10, generator=g)
     return torch.cat([cam, pose, shape], dim=1).float()
+
+
+def synthetic_hmr_inputs(batch, seed=9):
+    """-> images f32[B,3,224,224] in [-1,1] as HumanModelRecovery.forward receives them (models/imitator.py:93-95)."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(batch, 3, 28, 28, generator=g) * 2 - 1
+    img = torch.nn.functional.interpolate(low, size=(224, 224), mode='bilinear', align_corners=False)
+    return (img + 0.2 * (torch.rand(batch, 3, 224, 224, generator=g) - 0.5)).clamp(-1, 1)
+
+
+def synthetic_hmr_state(template, seed=4):
+    """Deterministic ``resnet.*`` / ``regressor.*`` entries for a HumanModelRecovery ``state_dict`` template (the
+    released hmr_tf2pt.pth is an external download; 27 M parameters are regenerated from the seed wherever needed).
+    He-scaled convs with the last conv of every residual branch damped (16 unit-gain branches would push the
+    pre-activation stream to |x| ~ 1e3), mean_theta like load_mean_theta (networks/hmr.py:190-211): scale 0.9, upright."""
+    sd = fill_state_dict({k: v for k, v in template.items() if not k.startswith("smpl.")}, seed=seed, conv_std='he')
+    mt = torch.zeros(85)
+    mt[0], mt[3] = 0.9, math.pi
+    mt[75:] = 0.1 * torch.randn(10, generator=torch.Generator().manual_seed(seed))
+    sd["regressor.mean_theta"] = mt
+    sd["regressor.fc_blocks.fc3.weight"] = sd["regressor.fc_blocks.fc3.weight"] * 0.03    # small_xavier (hmr.py:231)
+    for k in sd:
+        if sd[k].dim() == 4 and ".conv3." in k:
+            sd[k] = sd[k] * 0.25
+    return sd
+
+
+def write_synthetic_assets(root, image_size=256, n_targets=3, seed=0):
+    """Everything ``Imitator(opt)`` loads from disk in the reference, as synthetic files with the real formats
+    (README.md:48-68 lists the real downloads): under ``root``
+
+      assets/pretrains/smpl_faces.npy       int faces [13776, 3]                       utils/nmr.py:137
+      assets/pretrains/mapper.txt           obj-style v / vn / vt / f a/b/c records     utils/mesh.py:28-79
+      assets/pretrains/front_facial.json, head.json    {"face": [...]}                  utils/mesh.py:327-365
+      assets/pretrains/smpl_model.pkl       protocol-2 pickle (keys of batch_smpl.py:236-283)
+      assets/pretrains/hmr_tf2pt.pth        HumanModelRecovery.state_dict()             models/imitator.py:69-74
+      outputs/checkpoints/G.pth             ImpersonatorGenerator.state_dict()          models/imitator.py:58-59
+      src.png, targets/000.png ...          source / driving frames
+
+    -> dict of paths.  Deterministic in ``seed``."""
+    import json
+    import os
+    import pickle
+    import cv2
+    from .generator import ImpersonatorGenerator
+    from .hmr import HumanModelRecovery
+    pre = os.path.join(root, "assets", "pretrains")
+    os.makedirs(pre, exist_ok=True)
+    os.makedirs(os.path.join(root, "outputs", "checkpoints"), exist_ok=True)
+    os.makedirs(os.path.join(root, "targets"), exist_ok=True)
+    v, f = uv_sphere()
+    np.save(os.path.join(pre, "smpl_faces.npy"), f.numpy())
+    rs = np.random.RandomState(seed)
+    nvt = 7576                                                     # SMPL's uv vertex count
+    vts = rs.rand(nvt, 2)
+    fvt = rs.randint(1, nvt + 1, size=(SMPL_F, 3))
+    with open(os.path.join(pre, "mapper.txt"), "w") as fp:
+        for p in v.numpy():
+            fp.write("v %.6f %.6f %.6f\n" % tuple(p))
+        fp.write("vn 0.0 0.0 1.0\n")
+        for p in vts:
+            fp.write("vt %.6f %.6f\n" % tuple(p))
+        for tri, uv in zip(f.numpy() + 1, fvt):
+            fp.write("f %d/%d/1 %d/%d/1 %d/%d/1\n" % (tri[0], uv[0], tri[1], uv[1], tri[2], uv[2]))
+    head = sorted(rs.choice(SMPL_F, size=1200, replace=False).tolist())
+    front = sorted(rs.choice(head, size=500, replace=False).tolist())
+    json.dump({"face": front}, open(os.path.join(pre, "front_facial.json"), "w"))
+    json.dump({"face": head}, open(os.path.join(pre, "head.json"), "w"))
+    smpl = synthetic_smpl_model(seed=3)
+    with open(os.path.join(pre, "smpl_model.pkl"), "wb") as fp:
+        pickle.dump(smpl, fp, protocol=2)
+    hmr = HumanModelRecovery(smpl_model=smpl)
+    full = dict(hmr.state_dict())
+    full.update(synthetic_hmr_state(hmr.state_dict()))
+    torch.save(full, os.path.join(pre, "hmr_tf2pt.pth"))
+    gen = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    gsd = fill_state_dict(gen.state_dict(), seed=0)
+    torch.save({"module." + k if i % 2 else k: t for i, (k, t) in enumerate(gsd.items())},           # BaseModel._load_params strips it
+               os.path.join(root, "outputs", "checkpoints", "G.pth"))
+
+    def to_u8(img):                                               # [3,H,W] in [-1,1] -> BGR uint8 HWC
+        a = ((img.permute(1, 2, 0).numpy() + 1) * 127.5).round().clip(0, 255).astype(np.uint8)
+        return a[..., ::-1].copy()
+    cv2.imwrite(os.path.join(root, "src.png"), to_u8(synthetic_source(image_size, seed=99)[0]))
+    tgt = []
+    for i in range(n_targets):
+        pth = os.path.join(root, "targets", "%03d.png" % i)
+        cv2.imwrite(pth, to_u8(synthetic_source(320, seed=200 + i)[0]))       # another size: the loaders resize
+        tgt.append(pth)
+    return dict(root=root, src=os.path.join(root, "src.png"), targets=os.path.join(root, "targets"), target_files=tgt,
+                smpl_model=os.path.join(pre, "smpl_model.pkl"), hmr_model=os.path.join(pre, "hmr_tf2pt.pth"),
+                load_path=os.path.join(root, "outputs", "checkpoints", "G.pth"), generator_state=gsd, hmr_state=full)

@@ -228,6 +228,37 @@ int lwb_conv2d_direct_nchw(const float* x, const float* w, const float* bias,
 int lwb_gated_bn_nchw(const float* ab, int n, int c, int h, int w, int act,
                       const float* scale, const float* shift, float* out, lwb_stream_t stream);
 
+/* ---- background inpaintor glue (networks/inpaintor.py; once per source image) -----------------------------------
+ * Every GatedConv2dWithActivation (:12-47) = ONE conv-engine plan over the stacked [conv2d ; mask_conv2d] filters (cout =
+ * 2c, padded to x16) + this epilogue:  y = BN_eval(act(a + bias[ch]) * sigmoid(b + bias[c + ch])),  a = raw[..., ch],
+ * b = raw[..., c + ch].  act: 0 none, 2 LeakyReLU(0.2).  upsample 2: y is written to the 2x2 block of every pixel of a
+ * [2h, 2w] grid = the nearest-neighbour resize GatedDeConv2dWithActivation convolves next (:65-68).  clamp: to [-1, 1]
+ * (:187,196).  Outputs (each nullable): y_f32 [n, h*u, w*u, f32_stride] (first c channels); the next layer's operands
+ * y_hi / y_lo [n, h*u, w*u, c_pad] with channels >= c zero (the engine's K chunks are 64 wide), lo_format as in
+ * lwb_norm_act_nhwc; range_flag as in lwb_norm_act_nhwc. */
+int lwb_gated_act_nhwc(const float* raw, int n, int h, int w, int c, int c_stride, const float* bias, int act,
+                       const float* scale, const float* shift, int upsample, int clamp,
+                       float* y_f32, int f32_stride, uint16_t* y_hi, uint16_t* y_lo, int c_pad, int lo_format,
+                       int* range_flag, lwb_stream_t stream);
+/* SelfAttention (networks/inpaintor.py:71-107) after the stacked 1x1 query / key / value convolution:
+ * qkv [n, npos, ld] fp32 rows = [q (dq) | k (dq) | v (dv) | pad], bias [2*dq + dv];
+ * out[i] = gamma[0] * sum_j softmax_j(q_i . k_j) v_j + x[i],  x / out [n, npos, dv] fp32.  dq = 16, dv = 128. */
+int lwb_self_attention_nhwc(const float* qkv, int ld, const float* bias, int n, int npos, int dq, int dv,
+                            const float* x, const float* gamma, float* out, lwb_stream_t stream);
+
+/* ---- HMR image encoder glue (networks/hmr.py:119-166, 214-252, 275-300) -----------------------
+ * The pre-activation ResNet-50's convolutions run on the conv engine above (lwb_conv_plan_*; eval-mode BatchNorm folded
+ * into lwb_norm_act_nhwc's per-channel affine); these three cover the rest, fp32:
+ *   F.max_pool2d(x, k, stride, ceil_mode=True) (hmr.py:150), x NCHW [n,c,h,w] -> out NHWC [n,ho,wo,c], ho = ceil((h-k)/stride)+1
+ *   relu?(x*scale+shift) averaged over the hw pixels (post_bn + ReLU + avg_pool2d(7), hmr.py:160-163), x NHWC [n,hw,c] ->
+ *     out[b*ld_out + ch]
+ *   nn.Linear (+ReLU) of the theta regressor (hmr.py:223-252): out[b*ld_out + j] (+)= relu?(x[b*ld_x + :k] . w[j,:k] + bias[j]) */
+int lwb_maxpool_nchw_to_nhwc(const float* x, int n, int c, int h, int w, int k, int stride, float* out, lwb_stream_t stream);
+int lwb_global_avgpool_nhwc(const float* x, int n, int hw, int c, const float* scale, const float* shift, int relu,
+                            float* out, int ld_out, lwb_stream_t stream);
+int lwb_linear(const float* x, int ld_x, const float* w, const float* bias, int n, int k, int m, int relu, int accumulate,
+               float* out, int ld_out, lwb_stream_t stream);
+
 /* ---- SMPL body model: pose -> vertices -------------------------------------------------
  * Replaces SMPL.forward (networks/batch_smpl.py:285-375; batch_rodrigues :64-101, batch_global_rigid_transformation
  * :129-218) as called by HumanModelRecovery.get_details (networks/hmr.py:302-330).

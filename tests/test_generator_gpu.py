@@ -181,3 +181,26 @@ def test_tensor_core_heads_equal_cuda_core_heads(cuda, net, monkeypatch):
     print("tensor-core heads vs CUDA-core heads: %.3e" % d)
     n._lwb_invalidate()
     assert d < 2e-4
+
+
+def test_sub_batch_streams_match_single_stream(cuda, net, monkeypatch):
+    """LWB_STREAMS=2: the batch runs as two sub-batches on side streams (their kernels overlap); same frames, same
+    results up to the order of the fp64 InstanceNorm atomics."""
+    n, sd = net
+    inp = S.synthetic_generator_inputs(4, 256, seed=33)
+    enc, res = n.encode_src(inp["src"].to(cuda))
+    bg = (torch.rand(1, 3, 256, 256) * 2 - 1).to(cuda)
+    tsf, T = inp["tsf"].to(cuda), inp["T"].to(cuda)
+    monkeypatch.setenv("LWB_STREAMS", "1")
+    c1, m1, p1 = [t.clone() for t in n.inference(enc, res, tsf, T, bg=bg)]
+    monkeypatch.setenv("LWB_STREAMS", "2")
+    hwc = torch.empty(4, 256, 256, 3, device=cuda)
+    u8 = torch.empty(4, 256, 256, 3, dtype=torch.uint8, device=cuda)
+    for _ in range(3):                                       # repeated: the side streams must be ordered against the caller's
+        c2, m2, p2 = n.inference(enc, res, tsf, T, bg=bg, pred_hwc=hwc, pred_u8=u8)
+    torch.cuda.synchronize()
+    d = max((c1 - c2).abs().max().item(), (m1 - m2).abs().max().item(), (p1 - p2).abs().max().item())
+    print("two sub-batch streams vs one: %.3e" % d)
+    assert d < 1e-5
+    assert torch.equal(hwc, p2.permute(0, 2, 3, 1))
+    assert n.range_status() == 0
