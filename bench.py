@@ -277,7 +277,8 @@ def main():
     else:
         src_img = torch.zeros_like(src_img)
     from impersonator_b200 import sharding
-    src_img = sharding.broadcast_module(net, extras=[src_img], src=0, device=dev)[0]      # the ONE collective
+    bc_stats = {}
+    src_img = sharding.broadcast_module(net, extras=[src_img], src=0, device=dev, stats=bc_stats)[0]      # the ONE collective
     net = net.to(dev).eval()
     render = SMPLRenderer(image_size=size, faces=f.numpy(), map_fn=tabs["map_fn"], has_front=False).to(dev)
 
@@ -359,6 +360,31 @@ def main():
     ms, launches = timed(step_device, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     fps = world * B * args.steps / (ms * 1e-3)
+    # ---- BASELINE configs[3] as written: a 64-frame stream sharded over the ranks (8 per GPU at N = 8), strong scaling:
+    # total work fixed, every rank runs its 64 / N frames in chunks of at most B; time = max over ranks
+    c3_frames = 64
+    c3 = None
+    if c3_frames % world == 0:
+        per_rank = c3_frames // world
+        a0, _ = sharding.shard_range(c3_frames, rank, world)
+        c3_sets = []
+        for k in range(0, per_rank, B):
+            nb = min(B, per_rank - k)
+            th = S.synthetic_smpl_params(c3_frames, seed=4242)[a0 + k:a0 + k + nb]
+            det = body.get_details(imitator.swap_smpl(imitator.src_info["cam"], imitator.src_info["shape"], th.to(dev), "smooth"))
+            c3_sets.append((det["cam"].contiguous(), det["verts"].contiguous()))
+
+        def step_c3(i):
+            out = None
+            for cam, verts in c3_sets:
+                o = render.correspond(cam, verts, p2v, simg)
+                out = net.inference(enc, res, o["tsf_inputs"], o["T"], bg=bg)[2]
+            return out
+        reps = 5
+        ms_c3, _ = timed(step_c3, reps, 3)
+        c3 = {"workload": "BASELINE configs[3]: 64-frame stream, %d frames per GPU on %d GPU(s), weights broadcast once" % (per_rank, world),
+              "frames": c3_frames, "frames_per_gpu": per_rank, "ms_per_64_frames": ms_c3 / reps,
+              "value": c3_frames / (ms_c3 / reps * 1e-3), "unit": "frames/s", "scaling": "strong"}
     steady = None
     if world == 1 and args.steady_steps > 0:
         # a long steady-state leg with its own clocks record (the driver's --steps 20 window is ~0.1 s)
@@ -400,6 +426,26 @@ def main():
             ms = t.item()
             dist.barrier()
         return ms
+    # ---- HMR image encoder (frames driven from video, tgt_smpls=None): ms per frame at batch B, device-resident images
+    hmr_leg = None
+    if rank == 0:
+        full = dict(body.state_dict())
+        full.update(S.synthetic_hmr_state(body.state_dict()))
+        body.load_state_dict(full)
+        body.eval()
+        imgs = S.synthetic_hmr_inputs(B).to(dev)
+        for _ in range(3):
+            body(imgs)
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(10):
+            body(imgs)
+        h1.record()
+        torch.cuda.synchronize()
+        hmr_leg = {"ms_per_frame": h0.elapsed_time(h1) / 10 / B, "batch": B,
+                   "what": "HumanModelRecovery.forward (pre-activation ResNet-50 @224^2 on the conv engine + 3-iteration regressor); "
+                           "added per frame when Imitator.inference is driven from images (tgt_smpls=None)"}
     run_e2e(max(args.steps, 3), 0)                  # warm-up call of the same length (also warms the pinned-host allocator)
     ms_e2e = timed_call(lambda: run_e2e(args.steps, 1))
     e2e_fps = world * B * args.steps / (ms_e2e * 1e-3)
@@ -418,10 +464,13 @@ def main():
                     "ms_per_step": ms_e2e / args.steps,
                     "api": "ONE call Imitator.inference_by_smpls(steps x B host SMPL vectors) -> per chunk of B: H2D, SMPL LBS, raster, "
                            "generator, composite, D2H to pinned host (overlapping the next chunk) -> list of host float32 HxWx3 frames",
+                    "hmr": hmr_leg,
                     "uint8_frames": {"value": world * B * args.steps / (ms_u8 * 1e-3), "unit": "frames/s",
                                      "d2h_bytes_per_step": B * 3 * size * size,
                                      "note": "same call with as_uint8=True: the BGR uint8 images the reference writes to disk"}},
-            "gpu_launches": launches, "clocks": clocks, "steady_state": steady, "parity": parity,
+            "gpu_launches": launches, "clocks": clocks, "steady_state": steady, "parity": parity, "config3_stream64": c3,
+            "init_broadcast": {"bytes": bc_stats.get("bytes"), "ms": bc_stats.get("ms"),
+                               "what": "the ONE collective: generator weights + source image, rank 0 -> all (NCCL), outside the timed region"},
             "personalize": {"ms_per_source": personalize_ms,
                             "what": "Imitator.personalize: SMPL LBS + raster + BG net + encode_src (host-synchronous, mean of 3)"}}
 

@@ -38,15 +38,27 @@ def unpack_state(flat, layout):
     return out
 
 
-def broadcast_module(net, extras=(), src=0, device=None):
+def broadcast_module(net, extras=(), src=0, device=None, stats=None):
     """Make every rank's ``net`` (and ``extras`` tensors) equal to rank ``src``'s with ONE collective.
-    Works with NCCL (CUDA tensors) and gloo (CPU tensors).  Returns the received extras."""
+    Works with NCCL (CUDA tensors) and gloo (CPU tensors).  Returns the received extras.  ``stats`` (dict, optional)
+    receives ``bytes`` and, for CUDA tensors, ``ms`` = device time of the collective (CUDA events)."""
     sd = net.state_dict()
     flat, layout = pack_state(sd, extras)
     if device is not None:
         flat = flat.to(device)
+    if stats is not None:
+        stats["bytes"] = flat.numel() * flat.element_size()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.broadcast(flat, src=src)
+        if flat.is_cuda and stats is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            dist.broadcast(flat, src=src)
+            e1.record()
+            torch.cuda.synchronize()
+            stats["ms"] = e0.elapsed_time(e1)
+        else:
+            dist.broadcast(flat, src=src)
     got = unpack_state(flat, layout)
     new_sd = {k: got[k].to(sd[k].dtype) for k in sd.keys()}
     net.load_state_dict(new_sd)

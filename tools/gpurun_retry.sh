@@ -4,6 +4,6 @@ log=$1; shift; to=$1; shift
 for i in $(seq 1 40); do
   /usr/local/graft/bin/gpurun --timeout $to -- "$@" > $log 2>&1; rc=$?
   if [ $rc -ne 3 ]; then echo "gpurun rc=$rc" >> $log; exit $rc; fi
-  sleep 90
+  sleep 20
 done
 echo "gave up" >> $log
