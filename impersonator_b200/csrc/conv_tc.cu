@@ -39,7 +39,10 @@
 
 #include <new>
 
+#include <cuda_fp8.h>
+
 #include "common.cuh"
+#include "sample.cuh"
 
 namespace {
 
@@ -49,7 +52,21 @@ constexpr int A_BYTES = 128 * 128;
 constexpr int MAX_TAPS = 49;
 constexpr int NUM_THREADS = 192;                 // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
+// InstanceNorm (+ReLU, +residual, +LWB warp-add) fused into the conv epilogue (k_conv_tc2<.., FUSED = true>): the operands
+// of the NEXT layer leave the kernel directly, no fp32 raw tensor and no second pass over HBM.  See epilogue_fused_loop.
+struct FusedNorm {
+    const float* gamma; const float* beta; float eps; int relu;
+    const float* residual;                                // [n,h,w,c] fp32, nullable
+    const float* warp_src; int src_batch; const float* T; int th, tw, align_corners;      // nullable LWB source (NHWC fp32)
+    float* y_f32; __half* y_hi; uint8_t* y_lo; int lo_format;
+    int* range_flag;
+    int* counters;                                        // [n_img * n_tiles_n], zero before every run: tiles of a unit done
+    int tiles_per_image;
+    double inv_hw;
+};
+
 struct ConvParams {
+    FusedNorm fn;
     CUtensorMap a_hi[4];
     CUtensorMap a_lo[4];
     CUtensorMap w_hi;
@@ -327,6 +344,205 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
     }
 }
 
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint8_t cvt_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+
+// Fused epilogue (cta_group::2 kernel only).  A "unit" = (image, N tile): its InstanceNorm statistics need every M tile of
+// the image.  Each CTA (a) reduces its tile's per-channel sum / sum of squares out of TMEM and adds them to the global f64
+// statistics, (b) publishes "tile done" on the unit's counter and waits until all tiles_per_image tiles are in, (c) reads
+// the finished statistics, and (d) normalises its tile out of TMEM a second time, applying ReLU / residual / LWB warp-add and
+// writing the next layer's operands (fp16 hi + fp16 or e4m3-pair lo, optional fp32).
+// Why the wait cannot deadlock: the grid is persistent with one CTA per SM (all CTAs co-resident), tiles are taken in
+// rounds of gridDim.x, a unit is a run of consecutive tiles no longer than one round, so a CTA waiting on its round-r tile
+// depends only on statistics of rounds <= r of other CTAs plus round r+1 tiles of LOWER-numbered pairs -- which those pairs
+// reach through their own (earlier-ordered) waits; the MMA warp meanwhile fills the second TMEM accumulator.  The host
+// enables this mode only when tiles_per_image / 2 <= gridDim.x / 2 and never together with multi-stream sub-batches.
+template <int N_TILE>
+__device__ __forceinline__ void epilogue_fused_loop(const ConvParams& P, int warp, unsigned lane, const Sched& sch,
+                                                    uint32_t tmem_base, uint64_t* bar_tfull, uint64_t* bar_tempty,
+                                                    float2* s_stats, float2* s_ss)
+{
+    const FusedNorm& F = P.fn;
+    const int q = warp & 3;
+    const int row = q * 32 + (int)lane;
+    const int ty = row >> 3, tx = row & 7;
+    const int et = threadIdx.x - 64;                            // 0..127
+    constexpr int CW = 32;
+    int abuf = 0; uint32_t aphase = 0;
+    for (int sup = sch.first; sup < sch.total; sup += sch.step) {
+        int n_idx, m_idx;
+        sch.decode(sup, n_idx, m_idx);
+        const int img = m_idx / (P.tiles_y * P.tiles_x);
+        const int rem = m_idx % (P.tiles_y * P.tiles_x);
+        const int y = (rem / P.tiles_x) * TILE_H + ty, x = (rem % P.tiles_x) * TILE_W + tx;
+        const bool valid = y < P.dom_h && x < P.dom_w;
+        mbar_wait(bar_tfull + abuf, aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * N_TILE);
+        // ---- pass 1: per-channel sums of this tile -> global statistics
+#pragma unroll 1
+        for (int c = 0; c < N_TILE / CW; c++) {
+            uint32_t r[CW];
+            tmem_ld32(taddr + c * CW, r);
+            tmem_ld_wait();
+            float v[CW], v2[CW];
+#pragma unroll
+            for (int j = 0; j < CW; j++) { const float t = valid ? __uint_as_float(r[j]) * P.out_scale : 0.f; v[j] = t; v2[j] = t * t; }
+            const float s1 = warp_col_sums<CW>(v, lane);
+            const float s2 = warp_col_sums<CW>(v2, lane);
+            s_stats[q * N_TILE + c * CW + lane] = make_float2(s1, s2);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int col = et; col < N_TILE; col += 128) {
+            const float2 a = s_stats[col], b = s_stats[N_TILE + col], cc = s_stats[2 * N_TILE + col], d = s_stats[3 * N_TILE + col];
+            double* dst = P.stats + 2 * ((size_t)img * P.cout + (size_t)n_idx * N_TILE + col);
+            atomicAdd(dst, (double)((a.x + b.x) + (cc.x + d.x)));
+            atomicAdd(dst + 1, (double)((a.y + b.y) + (cc.y + d.y)));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // ---- publish + wait for the unit
+        if (et == 0) {
+            int* ctr = F.counters + img * P.n_tiles_n + n_idx;
+            atomicAdd(ctr, 1);
+            if (ld_acquire_gpu(ctr) < F.tiles_per_image) {
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(ctr) < F.tiles_per_image) {
+                    __nanosleep(64);
+                    if (clock64() - t0 > 4000000000ll) {
+                        printf("lwb conv_tc: fused InstanceNorm wait timed out (block %d, unit %d/%d, count %d of %d)\n",
+                               blockIdx.x, img, n_idx, ld_acquire_gpu(ctr), F.tiles_per_image);
+                        __trap();
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int col = et; col < N_TILE; col += 128) {
+            const int ch = n_idx * N_TILE + col;
+            const double* sp = P.stats + 2 * ((size_t)img * P.cout + ch);
+            const double mean = __ldcg(sp) * F.inv_hw;
+            double var = __ldcg(sp + 1) * F.inv_hw - mean * mean;
+            if (var < 0) var = 0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)F.eps));
+            const float g = F.gamma ? __ldg(F.gamma + ch) : 1.f, bt = F.beta ? __ldg(F.beta + ch) : 0.f;
+            s_ss[col] = make_float2(g * rstd, bt - (float)mean * g * rstd);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // ---- pass 2: normalise this thread's pixel, emit operands
+        const size_t pix = ((size_t)img * P.out_h + y) * P.out_w + x;          // fused plans have oy_mul = ox_mul = 1
+        lwb::Taps tp;
+        tp.m = 0;
+        if (F.warp_src && valid) {
+            float gx, gy;
+            lwb::flow_at(F.T + (size_t)img * F.th * F.tw * 2, F.th, F.tw, P.out_h, P.out_w, y, x, gx, gy);
+            lwb::make_taps(gx, gy, P.out_h, P.out_w, F.align_corners, tp);
+        }
+        const float* wsrc = F.warp_src ? F.warp_src + (size_t)(F.src_batch == 1 ? 0 : img) * P.out_h * P.out_w * P.cout : nullptr;
+        unsigned hmax = 0;
+#pragma unroll 1
+        for (int c = 0; c < N_TILE / CW; c++) {
+            uint32_t r[CW];
+            __syncwarp();                                       // tcgen05.ld is warp-collective: reconverge after the per-pixel branches
+            tmem_ld32(taddr + c * CW, r);
+            tmem_ld_wait();
+            if (!valid) continue;
+            const int ch0 = n_idx * N_TILE + c * CW;
+            float v[CW];
+#pragma unroll
+            for (int j = 0; j < CW; j++) {
+                const float2 ss = s_ss[c * CW + j];
+                float t = fmaf(__uint_as_float(r[j]) * P.out_scale, ss.x, ss.y);
+                v[j] = F.relu ? fmaxf(t, 0.f) : t;
+            }
+            if (F.residual) {
+                const float4* rp = reinterpret_cast<const float4*>(F.residual + pix * P.cout + ch0);
+#pragma unroll
+                for (int j = 0; j < CW / 4; j++) {
+                    const float4 t = __ldg(rp + j);
+                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                }
+            }
+            if (tp.m) {
+                const int offs[4] = {tp.o00, tp.o00 + 1, tp.o00 + P.out_w, tp.o00 + P.out_w + 1};
+                const float wt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+                float acc[CW];
+#pragma unroll
+                for (int j = 0; j < CW; j++) acc[j] = 0.f;
+#pragma unroll
+                for (int t4 = 0; t4 < 4; t4++) {
+                    if (tp.m & (1 << t4)) {
+                        const float4* sp4 = reinterpret_cast<const float4*>(wsrc + (size_t)offs[t4] * P.cout + ch0);
+#pragma unroll
+                        for (int j = 0; j < CW / 4; j++) {
+                            const float4 t = __ldg(sp4 + j);
+                            acc[4 * j] += t.x * wt[t4]; acc[4 * j + 1] += t.y * wt[t4];
+                            acc[4 * j + 2] += t.z * wt[t4]; acc[4 * j + 3] += t.w * wt[t4];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CW; j++) v[j] += acc[j];
+            }
+            if (F.y_f32) {
+                float4* o = reinterpret_cast<float4*>(F.y_f32 + pix * P.cout + ch0);
+#pragma unroll
+                for (int j = 0; j < CW / 4; j++) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (F.y_hi) {
+                __align__(16) __half hh[CW];
+#pragma unroll
+                for (int j = 0; j < CW; j++) hh[j] = __float2half_rn(v[j]);
+                const uint4* hv = reinterpret_cast<const uint4*>(hh);
+                uint4* oh = reinterpret_cast<uint4*>(F.y_hi + pix * P.cout + ch0);
+#pragma unroll
+                for (int j = 0; j < CW / 8; j++) {
+                    oh[j] = hv[j];
+                    hmax = __vmaxu2(hmax, __vmaxu2(__vmaxu2(hv[j].x & 0x7fff7fffu, hv[j].y & 0x7fff7fffu),
+                                                   __vmaxu2(hv[j].z & 0x7fff7fffu, hv[j].w & 0x7fff7fffu)));
+                }
+                if (F.y_lo && F.lo_format == 0) {
+                    __align__(16) __half ll[CW];
+#pragma unroll
+                    for (int j = 0; j < CW; j++) ll[j] = __float2half_rn(v[j] - __half2float(hh[j]));
+                    uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(F.y_lo) + pix * P.cout + ch0);
+#pragma unroll
+                    for (int j = 0; j < CW / 8; j++) ol[j] = reinterpret_cast<const uint4*>(ll)[j];
+                } else if (F.y_lo) {
+                    // e4m3 pair block of this pixel's 64-channel group: bytes [ch % 64] = e4m3(x / 16), [64 + ch % 64] = e4m3(x_lo * 2^10)
+                    __align__(16) uint8_t x8[CW];
+                    __align__(16) uint8_t l8[CW];
+#pragma unroll
+                    for (int j = 0; j < CW; j++) {
+                        x8[j] = cvt_e4m3(v[j] * (1.f / 16.f));
+                        l8[j] = cvt_e4m3((v[j] - __half2float(hh[j])) * 1024.f);
+                    }
+                    uint8_t* blk = F.y_lo + (pix * P.cout + (size_t)(ch0 & ~63)) * 2 + (ch0 & 63);
+                    reinterpret_cast<uint4*>(blk)[0] = reinterpret_cast<const uint4*>(x8)[0];
+                    reinterpret_cast<uint4*>(blk)[1] = reinterpret_cast<const uint4*>(x8)[1];
+                    reinterpret_cast<uint4*>(blk + 64)[0] = reinterpret_cast<const uint4*>(l8)[0];
+                    reinterpret_cast<uint4*>(blk + 64)[1] = reinterpret_cast<const uint4*>(l8)[1];
+                }
+            }
+        }
+        if (F.range_flag) {
+            const unsigned m = max(hmax & 0xffffu, hmax >> 16);
+            if (m >= 0x6400u) atomicOr(F.range_flag, m >= 0x7b53u ? 3 : 1);
+        }
+        // all TMEM reads of this buffer are complete: hand it back to the MMA warp (the leader's barrier collects both CTAs)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_cta0(smem_u32(bar_tempty + abuf)));
+        if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+    }
+}
+
 // ----------------------------------------------------------------------------------- kernel
 template <int N_TILE, bool SPLIT, int CL, int KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc(const __grid_constant__ ConvParams P)
@@ -498,7 +714,7 @@ struct Cfg2 {
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = Cfg<N_TILE, SPLIT>::TMEM_COLS;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + 4 * N_TILE * 2 * 4;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + 4 * N_TILE * 2 * 4 + N_TILE * 8;
 };
 
 __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, void* dst, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
@@ -523,7 +739,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  :: "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-template <int N_TILE, bool SPLIT>
+template <int N_TILE, bool SPLIT, bool FUSED>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2(const __grid_constant__ ConvParams P)
 {
     using C = Cfg2<N_TILE, SPLIT>;
@@ -535,6 +751,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2(const __grid_consta
     uint64_t* bar_tempty = bar_tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
     float2* s_stats = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+    float2* s_ss = s_stats + 4 * N_TILE;                       // [N_TILE] (scale, shift), fused mode
 
     const int warp = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
@@ -642,7 +859,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2(const __grid_consta
         }
     } else {
         // ================================ epilogue (both CTAs, own TMEM rows) ===========
-        epilogue_loop<N_TILE, 1, true>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
+        if constexpr (FUSED) epilogue_fused_loop<N_TILE>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats, s_ss);
+        else                 epilogue_loop<N_TILE, 1, true>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
     }
 
     tc_fence_before();
@@ -923,6 +1141,7 @@ struct Launch {
     int cl;
     int kc;
     bool two_sm;
+    bool fused;
     int grid;
 };
 
@@ -966,13 +1185,13 @@ int launch_cl(const Launch& L, cudaStream_t st)
     return LWB_OK;
 }
 
-template <int N_TILE, bool SPLIT>
+template <int N_TILE, bool SPLIT, bool FUSED = false>
 int launch_2sm(const Launch& L, cudaStream_t st)
 {
     using C = Cfg2<N_TILE, SPLIT>;
     static bool attr_set = false;
     if (!attr_set) {
-        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc2<N_TILE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc2<N_TILE, SPLIT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -986,7 +1205,7 @@ int launch_2sm(const Launch& L, cudaStream_t st)
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
-    LWB_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tc2<N_TILE, SPLIT>, L.p));
+    LWB_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tc2<N_TILE, SPLIT, FUSED>, L.p));
     LWB_LAUNCH_OK();
     return LWB_OK;
 }
@@ -995,6 +1214,7 @@ template <int N_TILE, bool SPLIT>
 int launch_one(const Launch& L, cudaStream_t st)
 {
     if (L.two_sm) {
+        if constexpr (SPLIT && N_TILE >= 128) { if (L.fused) return launch_2sm<N_TILE, SPLIT, true>(L, st); }
         if constexpr (N_TILE >= 64) return launch_2sm<N_TILE, SPLIT>(L, st);
     }
     if (L.kc == 32) return launch_cl<N_TILE, SPLIT, 1, 32>(L, st);
@@ -1121,7 +1341,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.f8 = f8 ? 1 : 0;
         p.out_scale = f8 ? ldexpf(1.f, -d->w_exp) : 1.f;      // weights are packed x 2^w_exp in f8 mode (lwb_pack_conv_weight_f8)
         L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl; L.kc = d->rowk ? KCHUNK : kc;
-        L.two_sm = two_sm;
+        L.two_sm = two_sm; L.fused = false;
         p.stages = 64;      // clamped to Cfg::STAGES at launch
         const long total_super = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n / cl;
         const long max_clusters = sms / cl;
@@ -1199,7 +1419,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         h.oy_mul = 1; h.ox_mul = 1; h.oy_add = 0; h.ox_add = 0;
         h.stats = stats;
         h.out_scale = 1.f;
-        L.n_tile = n_tile; L.split = split; L.cl = 1; L.two_sm = false;
+        L.n_tile = n_tile; L.split = split; L.cl = 1; L.two_sm = false; L.fused = false;
         const long total = (long)h.n_img * h.tiles_y * h.tiles_x * h.n_tiles_n;
         L.grid = (int)(total < sms ? total : sms);
         *plan_out = plan;
@@ -1307,6 +1527,37 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     L.p.oy_mul = 1; L.p.ox_mul = 1; L.p.oy_add = 0; L.p.ox_add = 0;
     finish(L, d->h_out, d->w_out);
     *plan_out = plan;
+    return LWB_OK;
+}
+
+extern "C" int lwb_conv_plan_fuse_norm(lwb_conv_plan* plan, const lwb_fused_norm* f)
+{
+    LWB_CHECK_ARG(plan && f, "null pointer");
+    if (plan->num != 1) { lwb::set_error("fuse_norm: multi-launch plans (transposed convs) keep the separate norm pass"); return LWB_E_UNSUPPORTED; }
+    Launch& L = plan->launches[0];
+    ConvParams& p = L.p;
+    if (L.halo || !L.two_sm || !L.split || L.n_tile < 128 || !p.stats || p.oy_mul != 1 || p.ox_mul != 1) {
+        lwb::set_error("fuse_norm: needs a split-mode cta_group::2 plan with N tile >= 128 and statistics");
+        return LWB_E_UNSUPPORTED;
+    }
+    const int tiles_per_image = p.tiles_y * p.tiles_x;
+    // every unit (image, N tile) must fit one round of the persistent grid (see epilogue_fused_loop)
+    if (tiles_per_image > L.grid || (tiles_per_image & 1)) {
+        lwb::set_error("fuse_norm: %d tiles per image exceed one round of the grid (%d CTAs)", tiles_per_image, L.grid);
+        return LWB_E_UNSUPPORTED;
+    }
+    LWB_CHECK_ARG(f->counters && (f->y_hi || f->y_f32), "fuse_norm: counters and an output are required");
+    LWB_CHECK_ARG(!f->warp_src || (f->T && f->th > 0 && f->tw > 0 && (f->src_batch == 1 || f->src_batch == p.n_img)), "bad warp arguments");
+    LWB_CHECK_ARG(f->lo_format == 0 || (f->lo_format == 1 && p.cout % 64 == 0), "lo_format 1 needs channels in blocks of 64");
+    FusedNorm& F = p.fn;
+    F.gamma = f->gamma; F.beta = f->beta; F.eps = f->eps; F.relu = f->relu;
+    F.residual = f->residual;
+    F.warp_src = f->warp_src; F.src_batch = f->src_batch; F.T = f->T; F.th = f->th; F.tw = f->tw; F.align_corners = f->align_corners;
+    F.y_f32 = f->y_f32; F.y_hi = (__half*)f->y_hi; F.y_lo = (uint8_t*)f->y_lo; F.lo_format = f->lo_format;
+    F.range_flag = f->range_flag;
+    F.counters = f->counters; F.tiles_per_image = tiles_per_image;
+    F.inv_hw = 1.0 / ((double)p.dom_h * p.dom_w);
+    L.fused = true;
     return LWB_OK;
 }
 

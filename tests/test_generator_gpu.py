@@ -204,3 +204,39 @@ def test_sub_batch_streams_match_single_stream(cuda, net, monkeypatch):
     assert d < 1e-5
     assert torch.equal(hwc, p2.permute(0, 2, 3, 1))
     assert n.range_status() == 0
+
+
+@pytest.mark.parametrize("mode", ["fp16f8", "fp16x3"])
+def test_fused_instance_norm_matches_separate_pass(cuda, net, monkeypatch, mode):
+    """LWB_FUSE_NORM=1: InstanceNorm + ReLU / residual / LWB warp-add inside the conv epilogue (lwb_conv_plan_fuse_norm) for
+    every layer up to 128 x 128 against the separate lwb_norm_act_nhwc pass: same statistics (f64 atomics), same arithmetic."""
+    n, sd = net
+    monkeypatch.setenv("LWB_PRECISION", mode)
+    inp = S.synthetic_generator_inputs(3, 256, seed=44)
+    src, tsf, T = inp["src"].to(cuda), inp["tsf"].to(cuda), inp["T"].to(cuda)
+    monkeypatch.setenv("LWB_FUSE_NORM", "0")
+    n._lwb_invalidate()
+    enc0, res0 = n.encode_src(src)
+    img0, mask0 = [t.clone() for t in n.inference(enc0, res0, tsf, T)]
+    e3, r5 = enc0[3].clone(), res0[5].clone()
+    monkeypatch.setenv("LWB_FUSE_NORM", "1")
+    n._lwb_invalidate()
+    enc1, res1 = n.encode_src(src)
+    fused_layers = sum(int(L.fusable) for st in n.tsf_model._lwb_streams.values() for L in st._layers) if n.tsf_model._lwb_streams else 0
+    for _ in range(2):                                        # twice: counters / statistics must be re-zeroed per pass
+        img1, mask1 = n.inference(enc1, res1, tsf, T)
+    torch.cuda.synchronize()
+    fused_layers = sum(int(L.fusable) for st in n.tsf_model._lwb_streams.values() for L in st._layers)
+    d = {"enc3": (enc1[3] - e3).abs().max().item(), "res5": (res1[5] - r5).abs().max().item(),
+         "img": (img1 - img0).abs().max().item(), "mask": (mask1 - mask0).abs().max().item()}
+    print("%s fused norm (%d fused layers in the tsf stream) vs separate pass: %s" % (mode, fused_layers, d))
+    n._lwb_invalidate()
+    assert fused_layers >= 15
+    assert max(d.values()) < 2e-5
+    g = np.load(os.path.join(GOLD, "generator.npz"))
+    inp2 = S.synthetic_generator_inputs(2, 256, seed=21)
+    monkeypatch.setenv("LWB_FUSE_NORM", "1")
+    enc, res = n.encode_src(inp2["src"].to(cuda))
+    img, mask = n.inference(enc, res, inp2["tsf"].to(cuda), inp2["T"].to(cuda))
+    assert np.abs(sl(img) - g["inf_tsf_img"]).max() < TOL and np.abs(sl(mask) - g["inf_tsf_mask"]).max() < TOL
+    n._lwb_invalidate()
