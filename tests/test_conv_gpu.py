@@ -27,7 +27,8 @@ def report(name, got, ref):
     return d.max().item() / scale
 
 
-def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x1=None, n_tile=0, stats=True, halo=False):
+def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x1=None, n_tile=0, stats=True, halo=False,
+             pad_w=None):
     """x [n,c,h,w] fp32 CPU, w OIHW (or IOHW when transposed) -> NCHW fp32 CPU result, stats."""
     n, c0, h, wd = x.shape
     if int(split) == 2:
@@ -40,7 +41,7 @@ def run_conv(cuda, x, w, stride=1, pad=1, dil=1, transposed=False, split=True, x
     kh, kw = w.shape[2:]
     d = K.make_conv_desc(n, h, wd, c0, cout, kh, kw, stride=stride, pad=pad, dil=dil,
                          cin1=0 if x1 is None else x1.shape[1], transposed=transposed, split=split, n_tile=n_tile,
-                         halo=halo)
+                         halo=halo, pad_w=pad_w)
     out = torch.full((n, d.h_out, d.w_out, cout), float("nan"), dtype=torch.float32, device=cuda)
     st = torch.zeros((n, cout, 2), dtype=torch.float64, device=cuda) if stats else None
     plan = K.ConvPlan(d, xs, x1s, ws, out, st)
@@ -306,3 +307,105 @@ def test_conv_homogeneity_and_batch_invariance_at_full_batch(cuda, split):
     assert torch.equal(y[0], y[15]) and torch.equal(y[0], y[7])
     ref = F.conv2d(x1, wt, padding=1)
     assert report("512->512 @32 batch 16 (image 0)", y[:1], ref) < (2e-4 if split == 1 else 3e-4)
+
+
+# Shapes the round-2 callers add: tiny images under one 16x8 tile (HMR layer3/4: 14x14, 7x7), 1x1 filters with up to 2048
+# input channels, N tile 32 (folded heads, gated 16-channel layers, q/k/v), dilation 16, 5x5, 4x4 stride 2.
+R2_CASES = [
+    # name, n, cin, cout, h, w, k, stride, pad, dil, n_tile
+    ("hmr_1x1_2048_512_7x7", 3, 2048, 512, 7, 7, 1, 1, 0, 1, 0),
+    ("hmr_3x3_512_512_7x7", 3, 512, 512, 7, 7, 3, 1, 1, 1, 0),
+    ("hmr_3x3_s2_256_256_14", 3, 256, 256, 14, 14, 3, 2, 1, 1, 0),
+    ("hmr_1x1_64_256_56", 1, 64, 256, 56, 56, 1, 1, 0, 1, 0),
+    ("hmr_3x3_s2_64_64_56", 2, 64, 64, 56, 56, 3, 2, 1, 1, 0),
+    ("n32_3x3_64_32", 1, 64, 32, 40, 24, 3, 1, 1, 1, 0),
+    ("attn_1x1_128_160", 1, 128, 160, 64, 64, 1, 1, 0, 1, 0),
+    ("inp_3x3_dil16_128_256", 1, 128, 256, 64, 64, 3, 1, 16, 16, 0),
+    ("inp_5x5_64_64", 1, 64, 64, 64, 64, 5, 1, 2, 1, 0),
+    ("inp_4x4_s2_64_128", 1, 64, 128, 64, 64, 4, 2, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("split", [1, 2])
+@pytest.mark.parametrize("case", R2_CASES, ids=[c[0] for c in R2_CASES])
+def test_conv2d_round2_shapes(cuda, case, split):
+    name, n, cin, cout, h, w, k, stride, pad, dil, n_tile = case
+    x = rnd(n, cin, h, w, seed=11)
+    wt = rnd(cout, cin, k, k, seed=12, scale=0.05)
+    ref = F.conv2d(x, wt, stride=stride, padding=pad, dilation=dil)
+    got, st = run_conv(cuda, x, wt, stride=stride, pad=pad, dil=dil, split=split, n_tile=n_tile)
+    rel = report(name + "/split%d" % split, got, ref)
+    assert rel < 3e-4
+    check_stats(st, ref)
+
+
+@pytest.mark.parametrize("split", [1, 2])
+def test_conv_7x1_folded_heads(cuda, split):
+    """The 7x7 heads as a 7x1 filter with N = 7 columns x 4 channels (generator.fold_head_weights) + the column sum in
+    lwb_heads_composite(folded_kw=7), against F.conv2d + tanh / sigmoid."""
+    from impersonator_b200.generator import fold_head_weights
+    n, h, w = 2, 48, 40
+    x = rnd(n, 64, h, w, seed=21)
+    w_img, w_att = rnd(3, 64, 7, 7, seed=22, scale=0.02), rnd(1, 64, 7, 7, seed=23, scale=0.02)
+    folded = fold_head_weights(w_img, w_att)
+    raw, _ = run_conv(cuda, x, folded, stride=1, pad=3, pad_w=0, split=split, n_tile=32, stats=False)
+    raw_nhwc = raw.permute(0, 2, 3, 1).contiguous().to(cuda)
+    color, mask, _ = K.heads_composite(raw_nhwc, None, folded_kw=7)
+    ref_c = torch.tanh(F.conv2d(x, w_img, padding=3))
+    ref_m = torch.sigmoid(F.conv2d(x, w_att, padding=3))
+    d = max((color.cpu() - ref_c).abs().max().item(), (mask.cpu() - ref_m).abs().max().item())
+    print("folded 7x1 heads split %d vs torch: %.3e" % (split, d))
+    assert d < 2e-4
+
+
+@pytest.mark.parametrize("variant", ["plain", "res_warp"])
+@pytest.mark.parametrize("split", [1, 2])
+def test_conv_fused_instance_norm(cuda, split, variant):
+    """lwb_conv_plan_fuse_norm against conv + lwb_norm_act_nhwc on the same operands: 512 -> 512 @32x32, batch 3 (24 tiles per
+    N tile: several CTAs wait on every unit), twice in a row (counters / statistics re-zeroed)."""
+    n, c, h, w = 3, 512, 32, 32
+    x = rnd(n, c, h, w, seed=41)
+    wt = rnd(c, c, 3, 3, seed=42, scale=0.03)
+    gamma, beta = (1 + 0.1 * rnd(c, seed=43)).to(cuda), (0.1 * rnd(c, seed=44)).to(cuda)
+    if int(split) == 2:
+        xs = to_f8_operands(cuda, x)
+    else:
+        xs = K.nchw_to_nhwc_split(x.to(cuda), split=True)
+    ws = K.pack_conv_weight(wt.to(cuda), split=split)
+    d = K.make_conv_desc(n, h, w, c, c, 3, 3, stride=1, pad=1, split=split)
+    lo_format = 1 if int(split) == 2 else 0
+    res = rnd(n, h, w, c, seed=45).to(cuda) if variant == "res_warp" else None
+    src = rnd(1, h, w, c, seed=46).to(cuda) if variant == "res_warp" else None
+    T = (torch.rand(n, 64, 64, 2, generator=torch.Generator().manual_seed(47)) * 2.4 - 1.2).to(cuda) if variant == "res_warp" else None
+
+    def outs():
+        return (torch.empty(n, h, w, c, device=cuda), torch.empty(n, h, w, c, dtype=torch.float16, device=cuda),
+                torch.empty(n, h, w, c, dtype=torch.float16, device=cuda))
+    # separate pass
+    raw = torch.empty(n, h, w, c, device=cuda)
+    st = torch.zeros(n, c, 2, dtype=torch.float64, device=cuda)
+    K.ConvPlan(d, xs, None, ws, raw, st).run()
+    y0, hi0, lo0 = outs()
+    wsb = torch.empty(n, c, 2, device=cuda)
+    K.norm_act_nhwc(raw, st, gamma, beta, variant == "plain", wsb, residual=res, warp_src=src, T=T, align_corners=True,
+                    y_f32=y0, y_hi=hi0, y_lo=lo0, lo_format=lo_format)
+    # fused
+    st1 = torch.zeros(n, c, 2, dtype=torch.float64, device=cuda)
+    ctr = torch.zeros(n * 4, dtype=torch.int32, device=cuda)
+    raw1 = torch.full((n, h, w, c), float("nan"), device=cuda)
+    plan = K.ConvPlan(d, xs, None, ws, raw1, st1)
+    y1, hi1, lo1 = outs()
+    ok = plan.fuse_norm(gamma, beta, variant == "plain", ctr, residual=res, warp_src=src, T=T, align_corners=True,
+                        y_f32=y1, y_hi=hi1, y_lo=lo1, lo_format=lo_format)
+    assert ok, "a 32x32 split-mode plan must be fusable"
+    for _ in range(2):
+        st1.zero_()
+        ctr.zero_()
+        plan.run()
+    torch.cuda.synchronize()
+    dy = (y1 - y0).abs().max().item()
+    print("fused norm %s split %d: y max-abs diff %.3e (scale %.2f)" % (variant, split, dy, y0.abs().max().item()))
+    assert dy < 1e-5
+    assert (hi1.float() - hi0.float()).abs().max().item() < 2e-3
+    assert float(lo1.view(torch.uint8).ne(lo0.view(torch.uint8)).float().mean()) < 0.01
+    assert int(ctr[:n * 2].max()) == 8 and int(ctr[:n * 2].min()) == 8          # every unit saw its 8 tiles
