@@ -530,6 +530,8 @@ def main():
         for k, v in sorted(prof["layers"].items()):
             if k.startswith("conv/"):
                 layers[k[5:]] = {"ms": round(v["ms"], 4), "n": v["n"], "tflops_algorithmic": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)}
+            elif k.startswith("heads/"):
+                layers["heads " + k[6:]] = {"ms": round(v["ms"], 4), "n": v["n"], "tflops_algorithmic": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)}
             elif k.startswith("norm/"):
                 layers["norm " + k[5:]] = {"ms": round(v["ms"], 4), "n": v["n"], "gbs": round(v["work"] / (v["ms"] * 1e-3) / 1e9, 0)}
         line["layers"] = layers

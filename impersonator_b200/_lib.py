@@ -134,6 +134,7 @@ def stream():
 
 
 def _chk_cuda(*ts):
+    cur = None
     for t in ts:
         if t is None:
             continue
@@ -141,3 +142,9 @@ def _chk_cuda(*ts):
             raise LwbError("expected a CUDA tensor (no CPU path)")
         if not t.is_contiguous():
             raise LwbError("expected a contiguous tensor")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the launch goes to the CURRENT device's stream: refuse instead of launching on the wrong GPU
+            raise LwbError("tensor lives on cuda:%d but the current device is cuda:%d: wrap the call in "
+                           "torch.cuda.device(%d) / torch.cuda.set_device" % (t.device.index, cur, t.device.index))

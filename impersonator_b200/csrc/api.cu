@@ -17,18 +17,25 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+int device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
 int sm_count()
 {
-    static int cached = -1;
-    if (cached < 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
+    static int cached[kMaxDevices] = {};
+    const int slot = device_slot();
+    if (cached[slot] <= 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot) == cudaSuccess && n > 0)
+            cached[slot] = n;
         else
             return 148;
     }
-    return cached;
+    return cached[slot];
 }
 
 bool pdl_enabled()

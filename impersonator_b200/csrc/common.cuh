@@ -26,7 +26,9 @@ void set_error(const char* fmt, ...);
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
-int sm_count();
+int sm_count();                      // of the current device
+constexpr int kMaxDevices = 64;
+int device_slot();                   // current device ordinal (clamped to kMaxDevices - 1): index of per-device caches
 
 // Programmatic dependent launch (LWB_PDL, default on): kernels launched through launch_pdl may be scheduled while the
 // previous kernel of the stream drains; each of them executes pdl_wait() before its first global-memory access and

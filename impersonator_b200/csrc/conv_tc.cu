@@ -1148,7 +1148,8 @@ struct Launch {
 template <int N_TILE, bool SPLIT>
 int launch_halo_one(const Launch& L, cudaStream_t st)
 {
-    static int attr_smem = 0;
+    static int attr_smem_dev[lwb::kMaxDevices] = {};          // function attributes are per device
+    int& attr_smem = attr_smem_dev[lwb::device_slot()];
     if (L.halo_smem > attr_smem) {
         LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_halo<N_TILE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.halo_smem));
         attr_smem = L.halo_smem;
@@ -1162,7 +1163,8 @@ template <int N_TILE, bool SPLIT, int CL, int KC>
 int launch_cl(const Launch& L, cudaStream_t st)
 {
     using C = Cfg<N_TILE, SPLIT, KC>;
-    static bool attr_set = false;
+    static bool attr_set_dev[lwb::kMaxDevices] = {};          // function attributes are per device
+    bool& attr_set = attr_set_dev[lwb::device_slot()];
     if (!attr_set) {
         LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<N_TILE, SPLIT, CL, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
@@ -1189,7 +1191,8 @@ template <int N_TILE, bool SPLIT, bool FUSED = false>
 int launch_2sm(const Launch& L, cudaStream_t st)
 {
     using C = Cfg2<N_TILE, SPLIT>;
-    static bool attr_set = false;
+    static bool attr_set_dev[lwb::kMaxDevices] = {};          // function attributes are per device
+    bool& attr_set = attr_set_dev[lwb::device_slot()];
     if (!attr_set) {
         LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc2<N_TILE, SPLIT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;

@@ -303,6 +303,7 @@ class _StreamBase(object):
         if L is not None and getattr(self, 'folded_kw', 7) == 7 and L.plan.desc.kw == 1:
             L.plan.flops = 2.0 * self.B * self.H * self.W * 49 * 64 * 4
             L.plan.label = "H7x7 64->4 @%d (7x1 filter, N = 7 cols x 4)" % self.H
+            L.plan.prof_class = "heads"
 
     def begin_pass(self):
         """Zero the InstanceNorm statistics and the range flag (one fill)."""

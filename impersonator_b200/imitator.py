@@ -32,6 +32,19 @@ from .generator import ImpersonatorGenerator
 from .nmr import SMPLRenderer
 
 
+def _on_device(fn):
+    """Run a method with the Imitator's device current: the kernels launch on the current device's stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if self.device.type == 'cuda' and self.device.index is not None and self.device.index != torch.cuda.current_device():
+            with torch.cuda.device(self.device):
+                return fn(self, *a, **k)
+        return fn(self, *a, **k)
+    return wrapped
+
+
 def morph(src_bg_mask, ks, mode='erode'):
     """utils/util.py:73-89: box-filter erode / dilate of a {0,1} mask [N,1,H,W] (border counts as 1 / 0)."""
     pad = ks // 2
@@ -177,6 +190,7 @@ class Imitator(object):
         return self.hmr.get_details(smpl)
 
     # ---- personalize (models/imitator.py:82-145) ----------------------------------------------
+    @_on_device
     @torch.no_grad()
     def personalize(self, src_path, src_smpl=None, output_path='', visualizer=None, src_img=None):
         size = self._opt.image_size
@@ -239,6 +253,7 @@ class Imitator(object):
             cam = tgt_cam
         return torch.cat([cam, pose, src_shape.expand(tgt_smpl.shape[0], -1)], dim=1)
 
+    @_on_device
     @torch.no_grad()
     def transfer_params_by_smpl(self, tgt_smpl, cam_strategy='smooth', t=0):
         """tgt_smpl [85] or [B,85]: one frame (reference) or a chunk of frames (batched fast path)."""
@@ -276,6 +291,7 @@ class Imitator(object):
         return tsf_inputs
 
     # ---- generator + composite (models/imitator.py:326-342) -----------------------------------
+    @_on_device
     @torch.no_grad()
     def forward(self, tsf_inputs, T, host_layout=None):
         """-> preds [B,3,H,W].  ``host_layout`` = dict(hwc=bool, u8=bool) additionally fills
@@ -310,6 +326,7 @@ class Imitator(object):
         bs = max(1, int(getattr(self._opt, 'batch_size', 1)))
         return [(i, min(n, i + bs)) for i in range(0, n, bs)]
 
+    @_on_device
     @torch.no_grad()
     def inference(self, tgt_paths, tgt_smpls=None, cam_strategy='smooth', output_dir='', visualizer=None, verbose=True,
                   as_uint8=False):

@@ -64,6 +64,7 @@ class ConvPlan(object):
         self.num_launches = 1
         self.flops = 0.0
         self.label = "emulated"
+        self.prof_class = "conv"
 
     def fuse_norm(self, *a, **k):
         return False
