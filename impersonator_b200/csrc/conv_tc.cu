@@ -82,6 +82,8 @@ struct ConvParams {
     int stages;                       // pipeline depth actually used (<= Cfg::STAGES; LWB_STAGES, diagnostic)
     int f8;                           // SPLIT stages hold [A_hi | A_lo8 | B_hi | B_lo8]: 1 f16 + 1 f8f6f4 MMA per K step
     float out_scale;                  // accumulator -> output (2^-w_exp in f8 mode, else 1)
+    int phase_cols;                   // > 0: merged transposed conv -- column block col / phase_cols = sub-pixel phase (a, b) =
+                                      // (ph >> 1, ph & 1) of output pixel (2y + a, 2x + b), channel = col % phase_cols
 };
 
 template <int N_TILE, bool SPLIT, int KC = KCHUNK>
@@ -285,6 +287,7 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
         const bool valid = y < P.dom_h && x < P.dom_w;
         float* optr = P.out + (((size_t)img * P.out_h + (P.oy_mul * y + P.oy_add)) * P.out_w + (P.ox_mul * x + P.ox_add)) * P.cout
                     + (size_t)n_idx * N_TILE;
+        const int out_w_c = P.out_w * P.cout;                   // one output row, in floats (merged transposed conv)
         mbar_wait(bar_tfull + abuf, aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * NACC * N_TILE);
@@ -309,6 +312,11 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
             }
             if (valid && P.out) {
                 float4* o = reinterpret_cast<float4*>(optr + c * CW);
+                if (P.phase_cols > 0) {
+                    const int col = n_idx * N_TILE + c * CW, ph = col / P.phase_cols;
+                    o = reinterpret_cast<float4*>(P.out + (((size_t)img * P.out_h + 2 * y) * P.out_w + 2 * x) * P.cout
+                                                  + (size_t)(ph >> 1) * out_w_c + (ph & 1) * P.cout + (col - ph * P.phase_cols));
+                }
 #pragma unroll
                 for (int j = 0; j < CW / 4; j++)
                     o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -334,7 +342,9 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int col = et; col < N_TILE; col += 128) {
                 const float2 a = s_stats[col], b = s_stats[N_TILE + col], cc = s_stats[2 * N_TILE + col], d = s_stats[3 * N_TILE + col];
-                double* dst = P.stats + 2 * ((size_t)img * P.cout + (size_t)n_idx * N_TILE + col);
+                int ch = n_idx * N_TILE + col;
+                if (P.phase_cols > 0) ch %= P.phase_cols;      // the four phases of a channel share its statistics
+                double* dst = P.stats + 2 * ((size_t)img * P.cout + ch);
                 atomicAdd(dst, (double)((a.x + b.x) + (cc.x + d.x)));
                 atomicAdd(dst + 1, (double)((a.y + b.y) + (cc.y + d.y)));
             }
@@ -1464,6 +1474,40 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     const uint64_t wd[3] = {(uint64_t)cin_total, (uint64_t)d->cout, (uint64_t)ntaps_w};
     const uint64_t ws[2] = {(uint64_t)cin_total * 2, (uint64_t)d->cout * cin_total * 2};
     const uint32_t wb[3] = {(uint32_t)kc, (uint32_t)(n_tile / cl), 1};
+
+    if (d->transposed == 2) {
+        // Merged transposed conv: ONE stride-1 pass over the input grid with the four taps (dy, dx) in {0,1}^2 and
+        // N = 4 x cout columns = the four sub-pixel phases (weights from the host in [tap][phase*cout + co][cin] layout,
+        // zero where a phase does not use a tap: 9 of 16 blocks are non-zero).  One launch, one read of every input tile.
+        LWB_CHECK_ARG(d->kh == 3 && d->kw == 3 && d->stride == 2 && d->pad == 1 && d->cin1 == 0, "transposed conv: only k3 s2 p1 op1");
+        LWB_CHECK_ARG(d->h_out == 2 * d->h_in && d->w_out == 2 * d->w_in, "transposed conv output must be 2x input");
+        const int ncols = 4 * d->cout;
+        n_tile = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
+        LWB_CHECK_ARG(d->cout % 32 == 0 && ncols % n_tile == 0, "merged transposed conv needs cout in multiples of 32");
+        two_sm = sms >= 2 && (m_tiles0 % 2 == 0);
+        { const char* e = getenv("LWB_2SM"); if (e && atoi(e) == 0) two_sm = false; }
+        cl = two_sm ? 2 : 1;
+        Launch& L = plan->launches[plan->num++];
+        memset(&L.p, 0, sizeof(L.p));
+        if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0, kc)) != LWB_OK) return fail(rc);
+        if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0, kc)) != LWB_OK) return fail(rc);
+        const uint64_t mwd[3] = {(uint64_t)cin_total, (uint64_t)ncols, 4};
+        const uint64_t mws[2] = {(uint64_t)cin_total * 2, (uint64_t)ncols * cin_total * 2};
+        const uint32_t mwb[3] = {(uint32_t)kc, (uint32_t)(n_tile / cl), 1};
+        if ((rc = encode_map(&L.p.w_hi, w_hi, 3, mwd, mws, mwb)) != LWB_OK) return fail(rc);
+        if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, mwd, mws, mwb)) != LWB_OK) return fail(rc);
+        for (int t = 0; t < 4; t++) { L.p.dy[t] = (signed char)(t >> 1); L.p.dx[t] = (signed char)(t & 1); L.p.tmap[t] = 0; L.p.wtap[t] = (short)t; }
+        L.p.ntaps = 4; L.p.chunks0 = d->cin0 / kc; L.p.chunks1 = 0;
+        L.p.oy_mul = 2; L.p.ox_mul = 2; L.p.oy_add = 0; L.p.ox_add = 0;
+        finish(L, d->h_in, d->w_in);
+        L.p.phase_cols = d->cout;
+        L.p.n_tiles_n = ncols / n_tile;
+        const long total_super = (long)L.p.n_img * L.p.tiles_y * L.p.tiles_x * L.p.n_tiles_n / cl;
+        const long max_clusters = sms / cl;
+        L.grid = (int)((total_super < max_clusters ? total_super : max_clusters) * cl);
+        *plan_out = plan;
+        return LWB_OK;
+    }
 
     if (d->transposed) {
         // ConvTranspose2d(k=3, s=2, p=1, output_padding=1): out[2i+a, 2j+b] gathers, per axis,

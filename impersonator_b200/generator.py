@@ -72,6 +72,29 @@ def _tc_heads():
     return os.environ.get("LWB_TC_HEADS", "1") != "0"
 
 
+def _convt_merge():
+    """LWB_CONVT_MERGE (default 1): ConvTranspose2d(k3, s2, p1, op1) layers with up to 128 output channels run as ONE
+    stride-1 pass with the four sub-pixel phases stacked on N (merge_transposed_weight) instead of four phase launches."""
+    return os.environ.get("LWB_CONVT_MERGE", "1") != "0"
+
+
+def merge_transposed_weight(wt):
+    """IOHW [cin, cout, 3, 3] of ConvTranspose2d(k=3, s=2, p=1, output_padding=1) -> OIHW [4*cout, cin, 2, 2]: output
+    channel block ph = 2a + b holds sub-pixel phase out[2y+a, 2x+b]; filter tap (dy, dx) reads in[y+dy, x+dx].
+    Per axis: phase 0 uses k=1 at d=0; phase 1 uses k=2 at d=0 and k=0 at d=1 (oy = 2*iy - 1 + ky); the other 7 of the 16
+    (phase, tap) blocks are zero."""
+    cin, cout = wt.shape[0], wt.shape[1]
+    k_of = ({0: 1}, {0: 2, 1: 0})
+    out = torch.zeros((4 * cout, cin, 2, 2), dtype=torch.float32, device=wt.device)
+    for a in range(2):
+        for b in range(2):
+            ph = 2 * a + b
+            for dy, ky in k_of[a].items():
+                for dx, kx in k_of[b].items():
+                    out[ph * cout:(ph + 1) * cout, :, dy, dx] = wt[:, :, ky, kx].t().float()
+    return out
+
+
 def fold_head_weights(w_img, w_att):
     """[3,64,7,7] + [1,64,7,7] -> [32, 64, 7, 1]: output channel kx*4 + co of the (7 x 1) filter = column kx of head co
     (networks/generator.py:126-134; rows 28..31 are zero)."""
@@ -249,14 +272,18 @@ class _StreamBase(object):
                                  rowk=True, row_pitch=row_pitch, halo=halo)
         else:
             L.w = None
-            L.wsrc = (wt, transposed)                   # packed in _finalize (one max|w| sync for the whole stream)
             cout = wt.shape[1] if transposed else wt.shape[0]
             kh, kw = wt.shape[2], wt.shape[3]
+            merged = bool(transposed and _convt_merge() and cout <= 128 and cout % 32 == 0 and (kh, kw) == (3, 3))
+            # packed in _finalize (one max|w| sync for the whole stream)
+            L.wsrc = (merge_transposed_weight(wt), False) if merged else (wt, transposed)
             cin0 = x0[0].shape[3]
             cin1 = x1[0].shape[3] if x1 is not None else 0
             d = K.make_conv_desc(self.B, h, w, cin0, cout, kh, kw, stride=stride,
                                  pad=(pad if pad is not None else conv.padding[0]),
                                  cin1=cin1, transposed=transposed, split=self.split, halo=halo, n_tile=n_tile, pad_w=pad_w)
+            if merged:
+                d.transposed = 2                        # lwb_conv_desc: merged-phase weights
         L.raw = self._raw_buf(d.h_out, d.w_out, cout)
         L.stats = (len(self._stats_slots), cout)
         self._stats_slots.append(cout)

@@ -130,7 +130,11 @@ typedef struct lwb_conv_desc {
     int cin0, cin1;           /* channels of input 0 / input 1 (virtual torch.cat, cin1 = 0 if single); x64 */
     int cout;                 /* multiple of 16 */
     int kh, kw, stride, pad, dil;
-    int transposed;           /* ConvTranspose2d(k=3, s=2, p=1, output_padding=1) when != 0 */
+    int transposed;           /* 1: ConvTranspose2d(k=3, s=2, p=1, output_padding=1) as four sub-pixel phase launches, weights
+                                 packed from IOHW (lwb_pack_conv_weight, transposed = 1).  2: the same layer as ONE stride-1
+                                 pass over the input grid: weights [4 taps (dy,dx)][4*cout][cin] (phase 2a+b of output pixel
+                                 (2y+a, 2x+b) in column block 2a+b; zero blocks where a phase does not use a tap), packed as
+                                 an ordinary OIHW [4*cout, cin, 2, 2] filter; cout % 32 == 0, cout <= 128 recommended */
     int split;                /* 1 = 3-pass fp16 split (parity mode), 0 = single pass ("fast"), 2 = fp16 main product +
                                  both small products in fp8 (lo operands from lwb_pack_conv_weight_f8 / lo_format 1) */
     int rowk;                 /* 1 = 7x7-stem row-K mode: input is a padded NHWC8 buffer (see conv_tc.cu) */

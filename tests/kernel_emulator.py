@@ -81,7 +81,13 @@ class ConvPlan(object):
             y = F.conv2d(x, w)
         else:
             x = x.permute(0, 3, 1, 2)
-            if kind:
+            if d.transposed == 2:
+                # merged transposed conv (lwb_conv_desc.transposed = 2): weights [4*cout, cin, 2, 2], tap (dy, dx) reads
+                # in[y+dy, x+dx] (zero beyond the border), column block 2a+b is output pixel (2y+a, 2x+b)
+                y4 = F.conv2d(F.pad(x, (0, 1, 0, 1)), w)
+                n_, c4, h_, w_ = y4.shape
+                y = y4.view(n_, 2, 2, c4 // 4, h_, w_).permute(0, 3, 4, 1, 5, 2).reshape(n_, c4 // 4, 2 * h_, 2 * w_)
+            elif kind:
                 y = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=1)
             else:
                 pw = d.pad_w if d.pad_w >= 0 else d.pad

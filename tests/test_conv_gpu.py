@@ -409,3 +409,28 @@ def test_conv_fused_instance_norm(cuda, split, variant):
     assert (hi1.float() - hi0.float()).abs().max().item() < 2e-3
     assert float(lo1.view(torch.uint8).ne(lo0.view(torch.uint8)).float().mean()) < 0.01
     assert int(ctr[:n * 2].max()) == 8 and int(ctr[:n * 2].min()) == 8          # every unit saw its 8 tiles
+
+
+@pytest.mark.parametrize("split", [1, 2])
+@pytest.mark.parametrize("cin,cout,h", [(128, 64, 32), (256, 128, 24)])
+def test_conv_transposed_merged_phases(cuda, split, cin, cout, h):
+    """lwb_conv_desc.transposed = 2: ConvTranspose2d(k3, s2, p1, op1) as ONE stride-1 pass with the four sub-pixel phases
+    stacked on N (generator.merge_transposed_weight), against F.conv_transpose2d; statistics shared by the four phases."""
+    from impersonator_b200.generator import merge_transposed_weight
+    n, w = 2, 40
+    x = rnd(n, cin, h, w, seed=51)
+    wt = rnd(cin, cout, 3, 3, seed=52, scale=0.05)
+    ref = F.conv_transpose2d(x, wt, stride=2, padding=1, output_padding=1)
+    xs = to_f8_operands(cuda, x) if split == 2 else K.nchw_to_nhwc_split(x.to(cuda), split=True)
+    ws = K.pack_conv_weight(merge_transposed_weight(wt.to(cuda)), split=split)
+    d = K.make_conv_desc(n, h, w, cin, cout, 3, 3, stride=2, pad=1, transposed=True, split=split)
+    d.transposed = 2
+    out = torch.full((n, 2 * h, 2 * w, cout), float("nan"), device=cuda)
+    st = torch.zeros(n, cout, 2, dtype=torch.float64, device=cuda)
+    plan = K.ConvPlan(d, xs, None, ws, out, st)
+    assert plan.num_launches == 1
+    plan.run()
+    torch.cuda.synchronize()
+    got = K.nhwc_to_nchw(out).cpu()
+    assert report("merged convT %d->%d split %d" % (cin, cout, split), got, ref) < 3e-4
+    check_stats(st.cpu(), ref)
