@@ -917,6 +917,7 @@ struct HaloParams {
     int oy_mul, oy_add, ox_mul, ox_add;
     double* stats;
     float out_scale;                  // always 1 (shared epilogue)
+    int phase_cols;                   // always 0 (shared epilogue)
 };
 
 constexpr int HALO_NA = 2;            // activation ring depth

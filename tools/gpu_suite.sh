@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU suite + smoke + bench variants (development loop; one gpurun call).
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 -x --deselect tests/test_run_imitator_gpu.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 900 --deselect tests/test_run_imitator_gpu.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_gpu.log
 timeout 600 python -m pytest tests/test_run_imitator_gpu.py -m gpu -q -s -p no:cacheprovider --timeout 500 > gpurun_out/pytest_run_imitator.log 2>&1; echo "run_imitator rc=$?"; tail -12 gpurun_out/pytest_run_imitator.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 summ() {
