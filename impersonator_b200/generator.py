@@ -585,7 +585,7 @@ def _stream_for(mod, cls, key, *args, **kw):
     if key in streams:
         streams[key] = streams.pop(key)                  # most recently used last
     else:
-        while len(streams) >= 4:                         # evict the least recently used shape only (each holds ~GBs at B=16)
+        while len(streams) >= 8:                         # evict the least recently used shape only (each holds ~GBs at B=16)
             streams.pop(next(iter(streams)))
         streams[key] = cls(mod, *args, **kw)
     return streams[key]

@@ -234,6 +234,7 @@ class Imitator(object):
         src_info['src_inputs'] = src_inputs
         src_info['feats'] = self.generator.encode_src(src_inputs)
         self.src_info = src_info
+        self.__dict__['_graphs'] = {}                    # captured chunk graphs hold the previous source's buffers
         if visualizer is not None:
             visualizer.vis_named_img('src', img)
             visualizer.vis_named_img('bg', src_info['bg'])
@@ -262,7 +263,7 @@ class Imitator(object):
         if tgt_smpl.dim() == 1:
             tgt_smpl = tgt_smpl[None, ...]
         if t == 0 and cam_strategy == 'smooth':
-            self.first_cam = tgt_smpl[0:1, 0:3].clone()
+            self._set_first_cam(tgt_smpl[0:1, 0:3])
         tsf_smpl = self.swap_smpl(src_info['cam'], src_info['shape'], tgt_smpl, cam_strategy=cam_strategy)
         tsf_info = self._details(tsf_smpl)
         out = self.render.correspond(tsf_info['cam'], tsf_info['verts'], src_info['p2verts'], src_info['img'],
@@ -274,6 +275,55 @@ class Imitator(object):
         tsf_info['T'] = out['T']
         self.tsf_info = tsf_info
         return out['tsf_inputs']
+
+    def _set_first_cam(self, cam):
+        """models/imitator.py:243-244, into a persistent buffer (a captured CUDA graph reads it at a fixed address)."""
+        buf = getattr(self, '_first_cam_buf', None)
+        if buf is None or buf.device != cam.device:
+            buf = self._first_cam_buf = torch.empty((1, 3), dtype=torch.float32, device=cam.device)
+        buf.copy_(cam)
+        self.first_cam = buf
+
+    def _chunk_pure(self, smpl, cam_strategy='smooth', hwc=True, u8=False):
+        """Everything one chunk of frames needs on the device, as a pure function of the SMPL vectors [B,85] (no host sync,
+        persistent or pool-allocated buffers only: capturable as a CUDA graph): camera swap, SMPL LBS, raster +
+        correspondence, generator + composite, output-path layouts, range-flag snapshot."""
+        src_info = self.src_info
+        tsf_smpl = self.swap_smpl(src_info['cam'], src_info['shape'], smpl, cam_strategy=cam_strategy)
+        tsf_info = self._details(tsf_smpl)
+        out = self.render.correspond(tsf_info['cam'], tsf_info['verts'], src_info['p2verts'], src_info['img'],
+                                     align_corners=self._ac)
+        tsf_info['fim'], tsf_info['wim'], tsf_info['cond'] = out['fim'], out['wim'], out['cond']
+        tsf_info['tsf_img'], tsf_info['T'] = out['tsf_img'], out['T']
+        self.tsf_info = tsf_info
+        preds = self.forward(out['tsf_inputs'], out['T'], host_layout=dict(hwc=hwc, u8=u8))
+        flag = self.generator.tsf_model.range_flag_tensor()            # operand-range bits of this chunk's pass
+        flag = flag.clone() if flag is not None else None              # snapshot: the next pass zeroes the live flag
+        return dict(tsf_info=tsf_info, preds=preds, hwc=self._out_hwc, u8=self._out_u8, flag=flag)
+
+    def _chunk_step(self, smpl, cam_strategy, hwc, u8):
+        """``_chunk_pure`` eagerly, or -- LWB_GRAPH, full chunks -- replayed from a CUDA graph captured once per
+        (batch, camera strategy, layouts, source).  Graph outputs are static buffers: the frames / flag are staged into fresh
+        tensors here so that the D2H of this chunk may overlap the next replay."""
+        from .graph import CapturedStep, graphs_enabled
+        B = smpl.shape[0]
+        bs = max(1, int(getattr(self._opt, 'batch_size', 1)))
+        if not graphs_enabled() or B != bs or getattr(self._opt, 'front_warp', False):
+            return self._chunk_pure(smpl, cam_strategy, hwc, u8)
+        graphs = self.__dict__.setdefault('_graphs', {})
+        key = (B, cam_strategy, bool(hwc), bool(u8), id(self.src_info), os.environ.get("LWB_PRECISION"),
+               os.environ.get("LWB_STREAMS"), self._ac, getattr(self.generator, '_lwb_precision', None))
+        step = graphs.get(key)
+        if step is None:
+            if len(graphs) >= 4:
+                graphs.pop(next(iter(graphs)))
+            step = graphs[key] = CapturedStep(lambda smpl: self._chunk_pure(smpl, cam_strategy, hwc, u8), dict(smpl=smpl))
+        res = step(smpl=smpl)
+        if not step.captured:
+            return res
+        self.tsf_info = res['tsf_info']
+        stage = lambda t: t.clone() if t is not None else None
+        return dict(tsf_info=res['tsf_info'], preds=res['preds'], hwc=stage(res['hwc']), u8=stage(res['u8']), flag=stage(res['flag']))
 
     @torch.no_grad()
     def transfer_params(self, tgt_path, tgt_smpl=None, cam_strategy='smooth', t=0):
@@ -376,22 +426,24 @@ class Imitator(object):
                                          original=originals.pop(a0 + j, None))
 
         for (a, b) in self._chunks(length):
-            smpls = chunk_smpls(a, b)
-            tsf_inputs = self.transfer_params_by_smpl(smpls, cam_strategy, t=a)
+            smpls = torch.as_tensor(chunk_smpls(a, b), dtype=torch.float32).to(self.device, non_blocking=True)
+            if smpls.dim() == 1:
+                smpls = smpls[None, ...]
+            if a == 0 and cam_strategy == 'smooth':
+                self._set_first_cam(smpls[0:1, 0:3])
             want_u8 = bool(as_uint8 or output_dir)
-            preds = self.forward(tsf_inputs, self.tsf_info['T'], host_layout=dict(hwc=not as_uint8, u8=want_u8))
+            res = self._chunk_step(smpls, cam_strategy, not as_uint8, want_u8)
+            out_hwc, out_u8, flag = res['hwc'], res['u8'], res['flag']
             if visualizer is not None:
-                visualizer.vis_named_img('pred_' + cam_strategy, preds)
-            flag = self.generator.tsf_model.range_flag_tensor()            # operand-range bits of this chunk's pass
-            flag = flag.clone() if flag is not None else None              # snapshot: the next pass zeroes the live flag
+                visualizer.vis_named_img('pred_' + cam_strategy, res['preds'])
             ready = torch.cuda.Event()
             ready.record(main)
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(ready)
-                h_f = self._to_host(self._out_hwc, sync=False) if not as_uint8 else None
-                h_u8 = self._to_host(self._out_u8, sync=False) if want_u8 else None
+                h_f = self._to_host(out_hwc, sync=False) if not as_uint8 else None
+                h_u8 = self._to_host(out_u8, sync=False) if want_u8 else None
                 h_flag = self._to_host(flag, sync=False) if flag is not None else None
-                for t in (self._out_hwc, self._out_u8, flag):
+                for t in (out_hwc, out_u8, flag):
                     if t is not None:
                         t.record_stream(self._copy_stream)
                 done = torch.cuda.Event()
@@ -439,10 +491,11 @@ class Imitator(object):
 
     def _last_frame_info(self):
         """tsf_info must describe the LAST frame (run_imitator.py:33-45 reads fim/T/tsf_img/cam/verts/wim)."""
-        info = self.tsf_info
+        info = dict(self.tsf_info)
         for k, v in list(info.items()):
-            if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] > 1:
-                info[k] = v[-1:]
+            if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] >= 1:
+                info[k] = v[-1:].clone()                 # own storage: the chunk buffers may belong to a replayed graph
+        self.tsf_info = info
 
     def _maybe_save(self, pred, tgt_path, output_dir, t, is_bgr_u8=False, original=None):
         """pred_<file> (+ gt_<file> = the driving frame resized, models/imitator.py:182-187); inference_by_smpls names

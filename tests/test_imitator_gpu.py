@@ -247,3 +247,38 @@ def test_imitator_uint8_and_saved_frames(cuda, tmp_path):
         assert saved is not None and saved.shape == (size, size, 3)
         expect = cv2.imdecode(cv2.imencode('.jpg', u8[1])[1], -1)                       # the same encoder, in memory
         assert np.array_equal(saved, expect)
+
+
+def test_imitator_graph_replay_matches_eager(cuda, monkeypatch):
+    """LWB_GRAPH: full chunks are replayed from a captured CUDA graph (SMPL LBS + raster + generator + composite); same frames
+    as the eager launch sequence, sequence after sequence (first_cam / source buffers are read at fixed addresses), and a new
+    source invalidates the graphs."""
+    from impersonator_b200.hmr import HumanModelRecovery
+    torch.set_grad_enabled(False)
+    size = 256
+    v, f = S.uv_sphere()
+    tabs = S.synthetic_tables()
+    net = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    net.load_state_dict(S.fill_state_dict(net.state_dict(), seed=0))
+    render = SMPLRenderer(image_size=size, faces=f.numpy(), map_fn=tabs["map_fn"])
+    body = HumanModelRecovery(smpl_model=S.synthetic_smpl_model(seed=3)).to(cuda)
+    opt = Opt()
+    opt.batch_size = 4
+    im = Imitator(opt, generator=net, hmr=body, render=render, device=cuda)
+    tgt_a, tgt_b = S.synthetic_smpl_params(10, seed=31), S.synthetic_smpl_params(8, seed=32)
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LWB_GRAPH", mode)
+        im.personalize("", src_smpl=S.synthetic_smpl_params(1, seed=5)[0].numpy(), src_img=S.synthetic_source(size))
+        a = im.inference_by_smpls(list(tgt_a.numpy()))                       # chunks 4, 4, 2 (the partial one runs eagerly)
+        b = im.inference_by_smpls(list(tgt_b.numpy()), as_uint8=True)        # another first_cam, another layout
+        im.personalize("", src_smpl=S.synthetic_smpl_params(1, seed=6)[0].numpy(), src_img=S.synthetic_source(size, seed=7))
+        c = im.inference_by_smpls(list(tgt_b.numpy()))
+        results[mode] = (a, b, c, im.tsf_info["T"].clone())
+        if mode == "1":
+            assert any(g.captured for g in im._graphs.values()), "the chunk graph was not captured"
+    for x, y in zip(results["0"][0] + results["0"][2], results["1"][0] + results["1"][2]):
+        assert np.abs(x - y).max() < 1e-5
+    for x, y in zip(results["0"][1], results["1"][1]):
+        assert np.abs(x.astype(np.int32) - y.astype(np.int32)).max() <= 1
+    assert torch.equal(results["0"][3], results["1"][3])

@@ -44,13 +44,17 @@ def test_pytorch_default_init(cuda):
 
 def trained_like(seed=0, gain=4.0):
     """Student-t conv weights with a per-layer std drawn log-uniformly from [0.02, 0.5] and a few |w| > 2 outliers;
-    InstanceNorm gains log-uniform in [1/gain, gain], biases N(0, 0.5)."""
+    InstanceNorm gains log-uniform in [1/gain, gain], biases N(0, 0.5).  The two 7x7 heads (no normalisation behind them)
+    get std in [0.004, 0.03] so that the pre-tanh / pre-sigmoid values stay O(1..10) as in a trained network -- with std 0.5
+    they would be ~50 and a 1e-4 relative error of ANY fp32 implementation already exceeds 1e-3 on the unsaturated pixels."""
     tmpl = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6).state_dict()
     g = torch.Generator().manual_seed(seed)
     sd = {}
     for k, t in tmpl.items():
         if t.dim() == 4:
             std = float(0.02 * (25.0 ** torch.rand(1, generator=g)))
+            if "img_reg" in k or "attetion_reg" in k:
+                std = float(0.004 * (7.5 ** torch.rand(1, generator=g)))
             w = torch.distributions.StudentT(4.0).sample(t.shape) * std / 1.414
             idx = torch.randint(0, w.numel(), (8,), generator=g)
             w.view(-1)[idx] = torch.sign(w.view(-1)[idx]) * (2.0 + 3.0 * torch.rand(8, generator=g))
@@ -67,8 +71,12 @@ def test_trained_like_heavy_tailed_weights(cuda):
     torch.manual_seed(1)
     sd = trained_like(seed=0)
     assert max(v.abs().max().item() for v in sd.values() if v.dim() == 4) > 2.0        # the old packing would have raised
-    _, d, status, _ = _run(cuda, sd)
-    print("trained-like:", d, "range", status)
+    n, d, status, (inp, sd, img_o, mask_o) = _run(cuda, sd)
+    print("trained-like (fp16f8):", d, "range", status)
+    n.set_precision("fp16x3")
+    enc, res = n.encode_src(inp["src"].to(cuda))
+    img, mask = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda))
+    print("trained-like (fp16x3): img %.3e mask %.3e" % ((img.cpu() - img_o).abs().max().item(), (mask.cpu() - mask_o).abs().max().item()))
     assert d["img"] < TOL and d["mask"] < TOL and d["enc3_rel"] < TOL and d["res5_rel"] < TOL
     assert status == 0
 
