@@ -289,12 +289,34 @@ def main():
     imitator = Imitator(Opt(), generator=net, hmr=body, render=render, device=dev)
     src_theta = S.synthetic_smpl_params(1, seed=5)[0]
     imitator.personalize("", src_smpl=src_theta.numpy(), src_img=src_img)           # once per source (untimed)
-    torch.cuda.synchronize()
-    t0 = time.time()
-    for _ in range(3):
+    pers = []
+    for _ in range(6):
+        torch.cuda.synchronize()
+        t0 = time.time()
         imitator.personalize("", src_smpl=src_theta.numpy(), src_img=src_img)
-    torch.cuda.synchronize()
-    personalize_ms = (time.time() - t0) / 3 * 1e3
+        torch.cuda.synchronize()
+        pers.append((time.time() - t0) * 1e3)
+    personalize_ms = sorted(pers[1:])[2]                                            # median of 5 after one more warm call
+    inpaint_ms = None
+    if rank == 0 and not args.no_extras:
+        # the DeepFill-v2 background network (opt.bg_model != 'ORIGINAL', models/imitator.py:48-52,125) on the conv engine
+        from impersonator_b200.inpaintor import InpaintSANet
+        inp_net = InpaintSANet(c_dim=4)
+        inp_net.load_state_dict(S.fill_state_dict(inp_net.state_dict(), seed=3, conv_std=0.05))
+        inp_net = inp_net.to(dev).eval()
+        msk = torch.zeros(1, 1, size, size, device=dev)
+        msk[:, :, size // 4:3 * size // 4, size // 3:2 * size // 3] = 1
+        for _ in range(3):
+            inp_net(src_img.to(dev), msk, only_x=True)
+        torch.cuda.synchronize()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for _ in range(10):
+            inp_net(src_img.to(dev), msk, only_x=True)
+        i1.record()
+        torch.cuda.synchronize()
+        inpaint_ms = i0.elapsed_time(i1) / 10
+        del inp_net
 
     # per-step target frames: 4 rotating sets per rank, resident in HBM for `value`
     def thetas(seed):
@@ -485,8 +507,8 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "steady_state": steady, "parity": parity, "config3_stream64": c3,
             "init_broadcast": {"bytes": bc_stats.get("bytes"), "ms": bc_stats.get("ms"),
                                "what": "the ONE collective: generator weights + source image, rank 0 -> all (NCCL), outside the timed region"},
-            "personalize": {"ms_per_source": personalize_ms,
-                            "what": "Imitator.personalize: SMPL LBS + raster + BG net + encode_src (host-synchronous, mean of 3)"}}
+            "personalize": {"ms_per_source": personalize_ms, "inpaintor_ms_per_source": inpaint_ms,
+                            "what": "Imitator.personalize: SMPL LBS + raster + BG net + encode_src (host-synchronous wall clock, median of 5)"}}
 
     # ---- roofline of the conv engine + per-kernel-class breakdown (instrumented passes, rank 0) ---
     if rank == 0 and not args.no_extras:

@@ -81,6 +81,23 @@ def test_stock_torch_and_reference_kernels_vs_this_library(cuda):
         r = SMPLRenderer(image_size=size, faces=f, map_fn=tabs["map_fn"]).to(cuda)
         cam_d, verts_d = cam.to(cuda), verts.to(cuda)
         out["lwb_render_fim_wim_ms"] = timeit(lambda: r.render_fim_wim(cam_d, verts_d))
+    # --- InpaintSANet (once per source): the reference module's ATen ops (cuDNN / cuBLAS) vs the conv-engine stream ----------
+    from impersonator_b200.inpaintor import InpaintSANet
+    from oracle import inpaintor_ref as IR
+    inet = InpaintSANet(c_dim=4)
+    isd = S.fill_state_dict(inet.state_dict(), seed=3, conv_std=0.05)
+    inet.load_state_dict(isd)
+    inet = inet.to(cuda).eval()
+    isd_gpu = {k: v.to(cuda) for k, v in isd.items()}
+    img1 = S.synthetic_source(size, seed=5).to(cuda)
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, size), torch.linspace(-1, 1, size), indexing="ij")
+    msk = (((xs / 0.4) ** 2 + (ys / 0.8) ** 2) < 1).float()[None, None].to(cuda)
+    _, x_ref, _ = IR.forward(img1, msk, isd_gpu)
+    x_lwb = inet(img1, msk, only_x=True)
+    out["inpaintor_lwb_vs_stock_fp32_max_abs"] = (x_lwb - x_ref).abs().max().item()
+    out["inpaintor_stock_ms_fp32"] = timeit(lambda: IR.forward(img1, msk, isd_gpu), iters=5, warm=2)
+    out["inpaintor_lwb_ms"] = timeit(lambda: inet(img1, msk, only_x=True), iters=10, warm=3)
+    assert out["inpaintor_lwb_vs_stock_fp32_max_abs"] < 1e-3
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "stock_compare.json"), "w"), indent=1)
