@@ -532,7 +532,7 @@ def main():
                 os.environ.pop("LWB_STREAMS", None)
             else:
                 os.environ["LWB_STREAMS"] = had_streams
-        line["streams"] = {"LWB_STREAMS": os.environ.get("LWB_STREAMS", "1"),
+        line["streams"] = {"LWB_STREAMS": os.environ.get("LWB_STREAMS", "2 (default)"),
                            "cuda_graph": bool(captured is not None and captured.captured),
                            "ms_per_step_single_stream": ms_serial / args.steps,
                            "note": "roofline / breakdown / layers are measured with the kernels serialised (one stream), like ncu; "

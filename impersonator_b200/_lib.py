@@ -66,7 +66,7 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "lwb_pack_head_weights": (_i, [_vp, _vp, _vp, _vp]),
     "lwb_conv7x7_heads_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
-    "lwb_heads_composite": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lwb_heads_composite": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lwb_frames_out": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "lwb_gated_bn_nchw": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lwb_smpl_workspace_bytes": (_sz, [_i]),

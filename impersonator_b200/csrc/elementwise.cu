@@ -384,7 +384,8 @@ __device__ __forceinline__ uint8_t to_u8(float x) {
 __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ raw, int n, int hw, int w, int c_stride, int folded_kw,
                                                const float* __restrict__ bg, int bg_batch,
                                                float* __restrict__ color, float* __restrict__ mask, float* __restrict__ pred,
-                                               float* __restrict__ pred_hwc, uint8_t* __restrict__ pred_u8_bgr)
+                                               float* __restrict__ pred_hwc, uint8_t* __restrict__ pred_u8_bgr,
+                                               int* __restrict__ range_flag)
 {
     lwb::pdl_wait();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,6 +403,13 @@ __global__ void __launch_bounds__(256) k_heads(const float* __restrict__ raw, in
         }
     } else {
         r = __ldg(reinterpret_cast<const float4*>(raw + (size_t)i * c_stride));
+    }
+    if (range_flag) {
+        // Output-head pre-activations of +-8 and more: the ~1e-4 end-to-end RELATIVE precision of the fp16f8 operand split is
+        // then no longer enough for 1e-3 on the (unsaturated) pixels -- report it (bit 2), the caller switches to fp16x3.
+        const float m = fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w)));
+        const bool big = !(m < 8.f);
+        if (__any_sync(__activemask(), big) && big && !(*reinterpret_cast<volatile int*>(range_flag) & 4)) atomicOr(range_flag, 4);
     }
     const float col[3] = {tanhf(r.x), tanhf(r.y), tanhf(r.z)};
     const float m = 1.f / (1.f + expf(-r.w));
@@ -588,7 +596,7 @@ extern "C" int lwb_norm_act_nhwc(const float* raw, const double* stats, const fl
 extern "C" int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride, int folded_kw,
                                    const float* bg, int bg_batch,
                                    float* color, float* mask, float* pred,
-                                   float* pred_hwc, uint8_t* pred_u8_bgr, lwb_stream_t stream)
+                                   float* pred_hwc, uint8_t* pred_u8_bgr, int* range_flag, lwb_stream_t stream)
 {
     LWB_CHECK_ARG(raw, "null pointer");
     LWB_CHECK_ARG(bg || (!pred && !pred_hwc && !pred_u8_bgr), "the composite outputs need bg");
@@ -596,7 +604,7 @@ extern "C" int lwb_heads_composite(const float* raw, int n, int h, int w, int c_
     LWB_CHECK_ARG(!bg || bg_batch == 1 || bg_batch == n, "bg_batch must be 1 or n");
     LWB_CHECK_ARG(folded_kw >= 0 && (folded_kw == 0 || ((folded_kw & 1) && folded_kw * 4 <= c_stride)), "bad folded_kw");
     LWB_CUDA_OK(lwb::launch_pdl(k_heads, dim3(lwb::ceil_div((long)n * h * w, 256)), dim3(256), 0, (cudaStream_t)stream,
-                                raw, n, h * w, w, c_stride, folded_kw, bg, bg_batch, color, mask, pred, pred_hwc, pred_u8_bgr));
+                                raw, n, h * w, w, c_stride, folded_kw, bg, bg_batch, color, mask, pred, pred_hwc, pred_u8_bgr, range_flag));
     return LWB_OK;
 }
 

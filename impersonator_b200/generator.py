@@ -41,13 +41,14 @@ def precision_mode():
 
 
 def _sub_batches(B, enc_w, res_w, bg):
-    """LWB_STREAMS (default 1): number of concurrent sub-batches ImpersonatorGenerator.inference splits a batch into.
-    Only when the source features / background are shared by the batch (the imitation case) and B divides evenly."""
+    """LWB_STREAMS (default 2, at most 2): number of concurrent sub-batches ImpersonatorGenerator.inference splits a batch
+    into.  Only when the source features / background are shared by the batch (the imitation case), B divides evenly and
+    every sub-batch keeps at least 4 frames."""
     try:
-        n = int(os.environ.get("LWB_STREAMS", "1"))
+        n = min(2, int(os.environ.get("LWB_STREAMS", "2")))        # measured on B200: 2 sub-batches +6 %; more were not validated
     except ValueError:
         n = 1
-    if n <= 1 or B % n or B // n < 2:
+    if n <= 1 or B % n or B // n < 4:
         return 1
     shared = all(t is None or t.shape[0] == 1 for t in list(enc_w) + list(res_w)) and (bg is None or bg.shape[0] == 1)
     return n if shared else 1
@@ -60,7 +61,7 @@ def _fuse_norm():
     if os.environ.get("LWB_FUSE_NORM", "0") != "1":
         return False
     try:
-        return int(os.environ.get("LWB_STREAMS", "1")) <= 1
+        return int(os.environ.get("LWB_STREAMS", "2")) <= 1
     except ValueError:
         return True
 
@@ -169,7 +170,9 @@ class NetworkBase(nn.Module):
 
     def range_flags(self):
         """-> list of int32[1] device tensors, one per live stream: bit 0 = an activation left the e4m3 correction
-        range (|x| >= 1024, fp16f8 precision degrades for those elements), bit 1 = the fp16 range (|x| >= 60000 / NaN)."""
+        range (|x| >= 1024, fp16f8 precision degrades for those elements), bit 1 = the fp16 range (|x| >= 60000 / NaN),
+        bit 2 = output-head pre-activations of +-8 and more in fp16f8 mode (its ~1e-4 relative end-to-end precision then
+        no longer guarantees 1e-3 on the pixels: use fp16x3)."""
         flags = []
         for m in self.modules():
             for st in getattr(m, '_lwb_streams', {}).values():
@@ -177,14 +180,16 @@ class NetworkBase(nn.Module):
         return flags
 
     def range_flag_tensor(self):
-        """One int32 device scalar = OR over the live streams' flags (values are 0, 1 or 3, so max == OR); None if no
-        stream exists yet.  No host sync."""
+        """One int32 device scalar = OR over the live streams' flags; None if no stream exists yet.  No host sync."""
         flags = self.range_flags()
         if not flags:
             return None
         if len(flags) == 1:
             return flags[0]
-        return torch.stack([f.reshape(()) for f in flags]).amax().reshape(1)
+        acc = flags[0].clone()
+        for f in flags[1:]:
+            acc |= f
+        return acc
 
     def range_status(self):
         """OR of range_flags() as a Python int (one device sync); streams reset their flag at the start of a pass."""
@@ -474,7 +479,8 @@ class _UnetStream(_StreamBase):
             self.head_layer.plan.run()
         else:
             K.conv7x7_heads_nhwc(self.d_out[-1].f32, self.w4, out=self.head_raw)
-        return K.heads_composite(self.head_raw, bg, want_color=want_color, want_mask=want_mask, folded_kw=self.folded_kw, **out)
+        return K.heads_composite(self.head_raw, bg, want_color=want_color, want_mask=want_mask, folded_kw=self.folded_kw,
+                                 range_flag=self.range_flag if self.split == 2 else None, **out)
 
     def encoder_outs_nchw(self):
         outs = []

@@ -462,8 +462,9 @@ class Imitator(object):
             if range_bits[0] & 2:
                 raise LwbError("generator activations exceed the fp16 range (|x| >= 6e4 or non-finite): the conv engine's "
                                "fp16 operands cannot represent them")
-            warnings.warn("lwb_b200: activations beyond the fp16f8 correction range (|x| >= 1024); switching this "
-                          "generator to LWB_PRECISION=fp16x3 and recomputing the sequence")
+            warnings.warn("lwb_b200: %s; switching this generator to LWB_PRECISION=fp16x3 and recomputing the sequence"
+                          % ("activations beyond the fp16f8 correction range (|x| >= 1024)" if range_bits[0] & 1 else
+                             "output-head pre-activations beyond +-8 (fp16f8's ~1e-4 relative precision would exceed 1e-3 on pixels)"))
             self.generator.set_precision("fp16x3")
             self._range_retry = True
             try:

@@ -393,7 +393,7 @@ def conv7x7_heads_nhwc(x, w4, out=None):
 
 
 def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, mask=None, pred=None,
-                    want_pred=True, pred_hwc=None, pred_u8=None, folded_kw=0):
+                    want_pred=True, pred_hwc=None, pred_u8=None, folded_kw=0, range_flag=None):
     """-> color, mask, pred (NCHW).  ``pred_hwc`` f32 [n,h,w,3] / ``pred_u8`` uint8 BGR [n,h,w,3]: caller-allocated
     output-path buffers filled by the same launch."""
     _chk_cuda(raw, bg, color, mask, pred, pred_hwc, pred_u8)
@@ -411,7 +411,7 @@ def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, m
     _count(1)
     with _Prof("heads", 0.0):
         check(lib().lwb_heads_composite(ptr(raw), n, h, w, cs, int(folded_kw), ptr(bg), bg.shape[0] if bg is not None else 0,
-                                        ptr(color), ptr(mask), ptr(pred), ptr(pred_hwc), ptr(pred_u8), stream()),
+                                        ptr(color), ptr(mask), ptr(pred), ptr(pred_hwc), ptr(pred_u8), ptr(range_flag), stream()),
               "lwb_heads_composite")
     return color, mask, pred
 

@@ -226,11 +226,13 @@ int lwb_conv7x7_heads_nhwc(const float* x, const float* w4, int n, int h, int w,
  * cv2.imwrite (utils/cv_utils.py:23-36: RGB->BGR, ((x+1)/2*255) in fp32, truncated).
  * folded_kw = 0: raw[...,0:4] are the four head channels.  folded_kw = kw (7): raw is the output of the 7x7 heads run on
  * the tensor cores as a kh x 1 filter whose N dimension carries the filter columns, raw[y,x',kx*4+co] (c_stride >= 4*kw);
- * the row sum  out[y,x,co] = sum_kx raw[y, x+kx-kw/2, kx*4+co]  happens here, before tanh / sigmoid. */
+ * the row sum  out[y,x,co] = sum_kx raw[y, x+kx-kw/2, kx*4+co]  happens here, before tanh / sigmoid.
+ * range_flag (nullable, device int): |= 4 when a head pre-activation reaches +-8 -- beyond that the ~1e-4 relative
+ * end-to-end precision of the split = 2 operand mode no longer guarantees 1e-3 on the pixels (use split = 1). */
 int lwb_heads_composite(const float* raw, int n, int h, int w, int c_stride, int folded_kw,
                         const float* bg, int bg_batch,
                         float* color, float* mask, float* pred,
-                        float* pred_hwc, uint8_t* pred_u8_bgr, lwb_stream_t stream);
+                        float* pred_hwc, uint8_t* pred_u8_bgr, int* range_flag, lwb_stream_t stream);
 
 /* The same output-path conversion for frames [n,3,h,w] NCHW fp32 that did not come straight out of the heads
  * (e.g. after Imitator.warp_front, models/imitator.py:338-342). */

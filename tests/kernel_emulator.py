@@ -256,7 +256,7 @@ def conv7x7_heads_nhwc(x, w4, out=None):
 
 
 def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, mask=None, pred=None, want_pred=True,
-                    pred_hwc=None, pred_u8=None, folded_kw=0):
+                    pred_hwc=None, pred_u8=None, folded_kw=0, range_flag=None):
     n, h, w, cs = raw.shape
     if folded_kw:
         r = torch.zeros(n, h, w, 4)

