@@ -10,16 +10,16 @@ timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/b
 timeout 900 python bench.py --steps 30 --warmup 5 > gpurun_out/bench.json 2>gpurun_out/bench.err; echo "bench rc=$?"
 NCU="ncu --clock-control none --profile-from-start off"
 BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras --no-parity --steady-steps 0 --profile-range"
-export LWB_STREAMS_PROFILE=1
-timeout 600 env LWB_STREAMS=1 $NCU --metrics gpu__time_duration.sum -c 200 --csv --log-file gpurun_out/launches_steady.csv $BENCH > gpurun_out/ncu_launch.log 2>&1; echo "launch list rc=$?"
+export LWB_GRAPH_PROFILE_NOTE=1   # ncu passes: eager launches on one stream (LWB_GRAPH=0 LWB_STREAMS=1), same kernels
+timeout 600 env LWB_STREAMS=1 LWB_GRAPH=0 $NCU --metrics gpu__time_duration.sum -c 200 --csv --log-file gpurun_out/launches_steady.csv $BENCH > gpurun_out/ncu_launch.log 2>&1; echo "launch list rc=$?"
 cap() {  # name, kernel regex, skip, count
-  timeout 900 env LWB_STREAMS=1 $NCU --set full --import-source on -k regex:"$2" -s $3 -c $4 -o gpurun_out/$1 -f $BENCH > gpurun_out/$1.log 2>&1
+  timeout 900 env LWB_STREAMS=1 LWB_GRAPH=0 $NCU --set full --import-source on -k regex:"$2" -s $3 -c $4 -o gpurun_out/$1 -f $BENCH > gpurun_out/$1.log 2>&1
   echo "$1 rc=$?"
   ncu -i gpurun_out/$1.ncu-rep --page raw --csv > gpurun_out/$1.raw.csv 2>/dev/null
   rm -f gpurun_out/$1.ncu-rep
 }
 # DRAM traffic of every conv launch of one step (roofline.traffic): cheap metrics pass
-timeout 600 env LWB_STREAMS=1 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:k_conv_tc -c 64 --csv --log-file gpurun_out/conv_traffic.csv $BENCH > gpurun_out/ncu_traffic.log 2>&1; echo "traffic rc=$?"
+timeout 600 env LWB_STREAMS=1 LWB_GRAPH=0 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:k_conv_tc -c 64 --csv --log-file gpurun_out/conv_traffic.csv $BENCH > gpurun_out/ncu_traffic.log 2>&1; echo "traffic rc=$?"
 cap conv_res "k_conv_tc2<256" 6 2
 cap conv_skip256 "k_conv_tc2<64" 1 1
 cap conv_heads "k_conv_tc<32" 0 1
