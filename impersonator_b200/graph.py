@@ -48,7 +48,9 @@ class CapturedStep(object):
         try:
             g = torch.cuda.CUDAGraph()
             n0 = K.launch_count()
-            with torch.cuda.graph(g):
+            # thread_local: other threads of the process (e.g. the NCCL watchdog of a torchrun job) may call the CUDA API
+            # while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 out = fn(**self.static_in)
             self.launches = K.launch_count() - n0
             self.graph, self.static_out = g, out
