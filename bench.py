@@ -355,8 +355,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, collective=True):
-        """collective=False: rank-local timing (the rank-0-only extras must not enter a barrier)."""
+    def timed(fn, steps, warmup, collective=True, profile=False):
+        """collective=False: rank-local timing (the rank-0-only extras must not enter a barrier).  profile: bracket the
+        timed steps with cudaProfilerStart/Stop (--profile-range, for `ncu --profile-from-start off`)."""
         for i in range(warmup):
             fn(i)
         if collective:
@@ -365,14 +366,14 @@ def main():
             torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         K.reset_launch_count()
-        if args.profile_range:
+        if profile:
             torch.cuda.profiler.start()
         e0.record()
         for i in range(steps):
             fn(warmup + i)
         e1.record()
         torch.cuda.synchronize()
-        if args.profile_range:
+        if profile:
             torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         launches = K.launch_count()
@@ -393,14 +394,14 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, launches = timed(step_device, args.steps, max(args.warmup, 3))
+    ms, launches = timed(step_device, args.steps, max(args.warmup, 3), profile=args.profile_range)
     clocks = sampler.stop() if rank == 0 else None
     fps = world * B * args.steps / (ms * 1e-3)
     # ---- BASELINE configs[3] as written: a 64-frame stream sharded over the ranks (8 per GPU at N = 8), strong scaling:
     # total work fixed, every rank runs its 64 / N frames in chunks of at most B; time = max over ranks
     c3_frames = 64
     c3 = None
-    if c3_frames % world == 0:
+    if c3_frames % world == 0 and not args.profile_range:
         per_rank = c3_frames // world
         a0, _ = sharding.shard_range(c3_frames, rank, world)
         c3_sets = []
@@ -464,7 +465,7 @@ def main():
         return ms
     # ---- HMR image encoder (frames driven from video, tgt_smpls=None): ms per frame at batch B, device-resident images
     hmr_leg = None
-    if rank == 0:
+    if rank == 0 and not args.profile_range:
         full = dict(body.state_dict())
         full.update(S.synthetic_hmr_state(body.state_dict()))
         body.load_state_dict(full)
