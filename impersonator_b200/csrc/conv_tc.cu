@@ -82,6 +82,11 @@ struct ConvParams {
     int stages;                       // pipeline depth actually used (<= Cfg::STAGES; LWB_STAGES, diagnostic)
     int f8;                           // SPLIT stages hold [A_hi | A_lo8 | B_hi | B_lo8]: 1 f16 + 1 f8f6f4 MMA per K step
     float out_scale;                  // accumulator -> output (2^-w_exp in f8 mode, else 1)
+    // y-halo schedule (k_conv_tc2y): taps re-ordered into groups that share the input view, dx and the channel chunk and whose
+    // dy are consecutive; the group's activation tile (TILE_H + cnt - 1 rows) is fetched ONCE and tap i reads it i rows down
+    int ngroups; unsigned char g_first[MAX_TAPS], g_cnt[MAX_TAPS];
+    int a_rows;                       // rows of the activation box = TILE_H + max group size - 1
+    int nb_stages;                    // weight ring depth
     int phase_cols;                   // > 0: merged transposed conv -- column block col / phase_cols = sub-pixel phase (a, b) =
                                       // (ph >> 1, ph & 1) of output pixel (2y + a, 2x + b), channel = col % phase_cols
 };
@@ -884,6 +889,191 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2(const __grid_consta
 }
 
 // =====================================================================================================
+// y-halo variant of the 2-CTA kernel (k_conv_tc2y).  The kernel above re-fetches the 16 x 8-pixel activation tile for every
+// filter tap: per K step a CTA writes 32 KB (A hi + lo) + its weight half by TMA and the MMAs read ~48-96 KB -- the SM's
+// 128 B/clk shared-memory port is the bound, the tensor pipe idles.  Taps that differ only in dy read
+// the SAME pixels shifted by whole image rows, and one image row of the tile (8 pixels x 128 B) is exactly one 1024-byte
+// SWIZZLE_128B atom: a tile of TILE_H + cnt - 1 rows fetched once serves all cnt taps of the group through the UMMA
+// descriptor's start address (+ i * 1024 B; the swizzle phase lives in address bits 7-9 and does not change).  For a 3x3
+// filter the activation fill drops to 18/48 of its bytes, for the 7-tap heads / stem to 22/112.
+//   A ring: NA = 2 entries of a_rows KB (x2 with lo);  full[s] in the leader (both CTAs' bytes), empty[s] per CTA
+//   B ring: nb_stages entries of N/2 weight rows (x2 with lo), one entry per tap
+// =====================================================================================================
+constexpr int Y_NA = 2;
+constexpr int Y_MAX_NB = 8;
+
+template <int N_TILE, bool SPLIT>
+struct CfgY {
+    static constexpr int B_HALF = (N_TILE / 2) * 128;
+    static constexpr int B_STAGE = B_HALF * (SPLIT ? 2 : 1);
+    static constexpr int RING_BYTES = 196 * 1024;
+    static constexpr int TMEM_COLS = Cfg<N_TILE, SPLIT>::TMEM_COLS;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int SMEM_BYTES = 1024 + RING_BYTES + BAR_BYTES + 4 * N_TILE * 2 * 4;
+};
+
+template <int N_TILE, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2y(const __grid_constant__ ConvParams P)
+{
+    using C = CfgY<N_TILE, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_plane = P.a_rows * 1024;                        // one of hi / lo
+    const int a_stage = a_plane * (SPLIT ? 2 : 1);
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + Y_NA * a_stage;
+    uint64_t* bar_afull = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
+    uint64_t* bar_aempty = bar_afull + Y_NA;
+    uint64_t* bar_bfull = bar_aempty + Y_NA;
+    uint64_t* bar_bempty = bar_bfull + Y_MAX_NB;
+    uint64_t* bar_tfull = bar_bempty + Y_MAX_NB;
+    uint64_t* bar_tempty = bar_tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+    float2* s_stats = reinterpret_cast<float2*>(smem + C::RING_BYTES + C::BAR_BYTES);
+
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int nb = P.nb_stages;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < Y_NA; s++) { mbar_init(bar_afull + s, 1); mbar_init(bar_aempty + s, 1); }
+            for (int s = 0; s < Y_MAX_NB; s++) { mbar_init(bar_bfull + s, 1); mbar_init(bar_bempty + s, 1); }
+            for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + b, 1); mbar_init(bar_tempty + b, 8); }
+            fence_barrier_init();
+            fence_proxy_async();
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    lwb::pdl_wait();
+    lwb::pdl_trigger();
+
+    const int nchunks = P.chunks0 + P.chunks1;
+    const int m_tiles = P.n_img * P.tiles_y * P.tiles_x;
+    const Sched sch = make_sched(m_tiles, P.n_tiles_n, 2);
+
+    if (warp == 0) {
+        // ================================ TMA producer (both CTAs) ======================
+        int sa = 0; uint32_t pa = 0;
+        int sb = 0; uint32_t pb = 0;
+        for (int sup = sch.first; sup < sch.total; sup += sch.step) {
+            int n_idx, m_idx;
+            sch.decode(sup, n_idx, m_idx);
+            const int img = m_idx / (P.tiles_y * P.tiles_x);
+            const int rem = m_idx % (P.tiles_y * P.tiles_x);
+            const int y0 = (rem / P.tiles_x) * TILE_H, x0 = (rem % P.tiles_x) * TILE_W;
+            const int nrow = n_idx * N_TILE + (int)rank * (N_TILE / 2);
+            for (int g = 0; g < P.ngroups; g++) {
+                const int t0 = P.g_first[g], cnt = P.g_cnt[g];
+                for (int chunk = 0; chunk < nchunks; chunk++) {
+                    const bool second = chunk >= P.chunks0;
+                    const int mi = second ? 1 : P.tmap[t0];
+                    const int c0 = (second ? chunk - P.chunks0 : chunk) * KCHUNK;
+                    mbar_wait(bar_aempty + sa, pa ^ 1);
+                    uint8_t* sta = a_ring + sa * a_stage;
+                    const uint32_t afullc = mapa_cta0(smem_u32(bar_afull + sa));
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(bar_afull + sa, 2u * (uint32_t)a_stage);
+                        tma_load_4d_2sm(&P.a_hi[mi], sta, afullc, c0, x0 + P.dx[t0], y0 + P.dy[t0], img);
+                        if (SPLIT) tma_load_4d_2sm(&P.a_lo[mi], sta + a_plane, afullc, c0, x0 + P.dx[t0], y0 + P.dy[t0], img);
+                    }
+                    __syncwarp();
+                    if (++sa == Y_NA) { sa = 0; pa ^= 1; }
+                    for (int i = 0; i < cnt; i++) {
+                        mbar_wait(bar_bempty + sb, pb ^ 1);
+                        uint8_t* stb = b_ring + sb * C::B_STAGE;
+                        const uint32_t bfullc = mapa_cta0(smem_u32(bar_bfull + sb));
+                        const int wt = P.wtap[t0 + i];
+                        if (elect_one()) {
+                            if (leader) mbar_expect_tx(bar_bfull + sb, 2u * (uint32_t)C::B_STAGE);
+                            tma_load_3d_2sm(&P.w_hi, stb, bfullc, chunk * KCHUNK, nrow, wt);
+                            if (SPLIT) tma_load_3d_2sm(&P.w_lo, stb + C::B_HALF, bfullc, chunk * KCHUNK, nrow, wt);
+                        }
+                        __syncwarp();
+                        if (++sb == nb) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) ==================
+        if (leader) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+            int sa = 0; uint32_t pa = 0;
+            int sb = 0; uint32_t pb = 0;
+            int abuf = 0; uint32_t aphase = 0;
+            for (int sup = sch.first; sup < sch.total; sup += sch.step) {
+                mbar_wait(bar_tempty + abuf, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(abuf * N_TILE);
+                uint32_t started = 0;
+                for (int g = 0; g < P.ngroups; g++) {
+                    const int cnt = P.g_cnt[g];
+                    for (int chunk = 0; chunk < nchunks; chunk++) {
+                        mbar_wait(bar_afull + sa, pa);
+                        tc_fence_after();
+                        const uint32_t a_base = a_ring_u + sa * a_stage;
+                        for (int i = 0; i < cnt; i++) {
+                            mbar_wait(bar_bfull + sb, pb);
+                            tc_fence_after();
+                            const uint32_t a_hi = a_base + (uint32_t)i * 1024u;        // tap i: the tile i image rows further down
+                            const uint32_t a_lo = a_hi + a_plane;
+                            const uint32_t b_hi = b_ring_u + sb * C::B_STAGE;
+                            const uint32_t b_lo = b_hi + C::B_HALF;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < KCHUNK / 16; k++) {
+                                    const uint64_t da = make_desc(a_hi + k * 32), db = make_desc(b_hi + k * 32);
+                                    umma_f16_2sm(d_tmem, da, db, idesc, (started | (uint32_t)k) ? 1u : 0u);
+                                    if (SPLIT && P.f8) {
+                                        umma_f8_2sm(d_tmem, make_desc(a_lo + k * 32), make_desc(b_lo + k * 32), idesc, 1u);
+                                    } else if (SPLIT) {
+                                        umma_f16_2sm(d_tmem, da, make_desc(b_lo + k * 32), idesc, 1u);
+                                        umma_f16_2sm(d_tmem, make_desc(a_lo + k * 32), db, idesc, 1u);
+                                    }
+                                }
+                                umma_commit_2sm(bar_bempty + sb, 3);            // weight slot free in BOTH CTAs
+                            }
+                            __syncwarp();
+                            started = 1;
+                            if (++sb == nb) { sb = 0; pb ^= 1; }
+                        }
+                        if (elect_one()) umma_commit_2sm(bar_aempty + sa, 3);   // activation slot free in BOTH CTAs
+                        __syncwarp();
+                        if (++sa == Y_NA) { sa = 0; pa ^= 1; }
+                    }
+                }
+                if (elect_one()) umma_commit_2sm(bar_tfull + abuf, 3);
+                __syncwarp();
+                if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        epilogue_loop<N_TILE, 1, true>(P, warp, lane, sch, tmem_base, bar_tfull, bar_tempty, s_stats);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================
 // Halo variant (stride-1 k x k convs, and the row-K stem): the activation tile is fetched ONCE per
 // 64-channel chunk together with its halo -- (16 + kh - 1) rows of 16 pixels (8 + kw - 1 <= 16) -- and
 // every filter tap reads a shifted window of that one shared-memory tile through the UMMA descriptor:
@@ -1153,6 +1343,7 @@ struct Launch {
     int kc;
     bool two_sm;
     bool fused;
+    bool yhalo;
     int grid;
 };
 
@@ -1225,8 +1416,34 @@ int launch_2sm(const Launch& L, cudaStream_t st)
 }
 
 template <int N_TILE, bool SPLIT>
+int launch_2sm_y(const Launch& L, cudaStream_t st)
+{
+    using C = CfgY<N_TILE, SPLIT>;
+    static bool attr_set_dev[lwb::kMaxDevices] = {};
+    bool& attr_set = attr_set_dev[lwb::device_slot()];
+    if (!attr_set) {
+        LWB_CUDA_OK(cudaFuncSetAttribute(k_conv_tc2y<N_TILE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = lwb::pdl_enabled() ? 2 : 1;
+    LWB_CUDA_OK(cudaLaunchKernelEx(&cfg, k_conv_tc2y<N_TILE, SPLIT>, L.p));
+    LWB_LAUNCH_OK();
+    return LWB_OK;
+}
+
+template <int N_TILE, bool SPLIT>
 int launch_one(const Launch& L, cudaStream_t st)
 {
+    if (L.two_sm && L.yhalo) {
+        if constexpr (N_TILE >= 32) return launch_2sm_y<N_TILE, SPLIT>(L, st);
+    }
     if (L.two_sm) {
         if constexpr (SPLIT && N_TILE >= 128) { if (L.fused) return launch_2sm<N_TILE, SPLIT, true>(L, st); }
         if constexpr (N_TILE >= 64) return launch_2sm<N_TILE, SPLIT>(L, st);
@@ -1260,6 +1477,45 @@ int launch(const Launch& L, cudaStream_t st)
     return LWB_E_UNSUPPORTED;
 }
 
+// y-halo schedule: sort the taps by (input view, dx, dy) and cut them into runs of consecutive dy.  Returns the activation box
+// rows (TILE_H + longest run - 1) and fills the group tables + the weight-ring depth, or 0 when the variant does not apply
+// (disabled, longest run 1, rings do not fit).
+int plan_yhalo(ConvParams& p, int n_tile, bool split)
+{
+    static int want = -1;
+    if (want < 0) { const char* e = getenv("LWB_YHALO"); want = e ? atoi(e) : 1; }
+    if (!want || p.ntaps < 2) return 0;
+    int order[MAX_TAPS];
+    for (int t = 0; t < p.ntaps; t++) order[t] = t;
+    auto key = [&](int t) { return ((int)p.tmap[t] << 16) + (((int)p.dx[t] + 128) << 8) + ((int)p.dy[t] + 128); };
+    for (int i = 1; i < p.ntaps; i++) {                      // insertion sort (<= 49 taps)
+        const int v = order[i];
+        int j = i - 1;
+        while (j >= 0 && key(order[j]) > key(v)) { order[j + 1] = order[j]; j--; }
+        order[j + 1] = v;
+    }
+    signed char dy[MAX_TAPS], dx[MAX_TAPS], tm[MAX_TAPS]; short wt[MAX_TAPS];
+    for (int i = 0; i < p.ntaps; i++) { dy[i] = p.dy[order[i]]; dx[i] = p.dx[order[i]]; tm[i] = p.tmap[order[i]]; wt[i] = p.wtap[order[i]]; }
+    int ng = 0, maxcnt = 1;
+    unsigned char first[MAX_TAPS], cnt[MAX_TAPS];
+    for (int i = 0; i < p.ntaps; i++) {
+        if (i > 0 && tm[i] == tm[i - 1] && dx[i] == dx[i - 1] && dy[i] == dy[i - 1] + 1 && cnt[ng - 1] < 7) { cnt[ng - 1]++; }
+        else { first[ng] = (unsigned char)i; cnt[ng] = 1; ng++; }
+        if (cnt[ng - 1] > maxcnt) maxcnt = cnt[ng - 1];
+    }
+    if (maxcnt < 2) return 0;
+    const int a_rows = TILE_H + maxcnt - 1;
+    const int a_stage = a_rows * 1024 * (split ? 2 : 1);
+    const int b_stage = (n_tile / 2) * 128 * (split ? 2 : 1);
+    int nb = (196 * 1024 - Y_NA * a_stage) / b_stage;
+    if (nb > Y_MAX_NB) nb = Y_MAX_NB;
+    if (nb < 3) return 0;
+    for (int i = 0; i < p.ntaps; i++) { p.dy[i] = dy[i]; p.dx[i] = dx[i]; p.tmap[i] = tm[i]; p.wtap[i] = wt[i]; }
+    for (int g = 0; g < ng; g++) { p.g_first[g] = first[g]; p.g_cnt[g] = cnt[g]; }
+    p.ngroups = ng; p.a_rows = a_rows; p.nb_stages = nb;
+    return a_rows;
+}
+
 int pick_n_tile(int cout, bool split, int forced)
 {
     if (forced > 0) return forced;
@@ -1279,19 +1535,20 @@ struct lwb_conv_plan {
 };
 
 // Plain NHWC activation map: dims [C, W, H, N].
-static int map_nhwc(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c, int kc = KCHUNK)
+static int map_nhwc(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c, int kc = KCHUNK, int rows = TILE_H)
 {
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
-    const uint32_t box[4] = {(uint32_t)kc, TILE_W, TILE_H, 1};
+    const uint32_t box[4] = {(uint32_t)kc, TILE_W, (uint32_t)rows, 1};
     return encode_map(m, base, 4, dims, str, box);
 }
 // Parity view (py, px) of an NHWC tensor for stride-2 convs: element (y', x') = input (2y'+py, 2x'+px).
-static int map_nhwc_parity(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c, int py, int px, int kc = KCHUNK)
+static int map_nhwc_parity(CUtensorMap* m, const uint16_t* base, int n, int h, int w, int c, int py, int px, int kc = KCHUNK,
+                           int rows = TILE_H)
 {
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)((w - px + 1) / 2), (uint64_t)((h - py + 1) / 2), (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)2 * c * 2, (uint64_t)2 * w * c * 2, (uint64_t)h * w * c * 2};
-    const uint32_t box[4] = {(uint32_t)kc, TILE_W, TILE_H, 1};
+    const uint32_t box[4] = {(uint32_t)kc, TILE_W, (uint32_t)rows, 1};
     return encode_map(m, base + ((size_t)py * w + px) * c, 4, dims, str, box);
 }
 
@@ -1328,7 +1585,9 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     if (d->halo) cl = 1;
     // 2-CTA MMA (cta_group::2, LWB_2SM=0 disables): pairs of M tiles share one weight tile, half of it per CTA
     bool two_sm = false;
+    bool want_2sm = true;
     { const char* e = getenv("LWB_2SM"); const int want = e ? atoi(e) : 1;
+      want_2sm = want != 0;
       two_sm = want && !d->halo && n_tile >= 64 && (m_tiles0 % 2 == 0) && sms >= 2;
       if (d->transposed && n_tile <= 64 && want != 2) two_sm = false;      // measured: 0.276 vs 0.240 ms on the 128->64 phases
     }
@@ -1355,7 +1614,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         p.f8 = f8 ? 1 : 0;
         p.out_scale = f8 ? ldexpf(1.f, -d->w_exp) : 1.f;      // weights are packed x 2^w_exp in f8 mode (lwb_pack_conv_weight_f8)
         L.n_tile = n_tile; L.split = split; L.halo = false; L.halo_smem = 0; L.cl = cl; L.kc = d->rowk ? KCHUNK : kc;
-        L.two_sm = two_sm; L.fused = false;
+        L.two_sm = two_sm; L.fused = false; L.yhalo = false;
         p.stages = 64;      // clamped to Cfg::STAGES at launch
         const long total_super = (long)p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n / cl;
         const long max_clusters = sms / cl;
@@ -1433,7 +1692,7 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         h.oy_mul = 1; h.ox_mul = 1; h.oy_add = 0; h.ox_add = 0;
         h.stats = stats;
         h.out_scale = 1.f;
-        L.n_tile = n_tile; L.split = split; L.cl = 1; L.two_sm = false; L.fused = false;
+        L.n_tile = n_tile; L.split = split; L.cl = 1; L.two_sm = false; L.fused = false; L.yhalo = false;
         const long total = (long)h.n_img * h.tiles_y * h.tiles_x * h.n_tiles_n;
         L.grid = (int)(total < sms ? total : sms);
         *plan_out = plan;
@@ -1462,7 +1721,18 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         L.p.ntaps = d->kh; L.p.chunks0 = 1; L.p.chunks1 = 0;
         for (int ky = 0; ky < d->kh; ky++) { L.p.dy[ky] = (signed char)ky; L.p.dx[ky] = 0; L.p.tmap[ky] = 0; L.p.wtap[ky] = (short)ky; }
         L.p.oy_mul = 1; L.p.ox_mul = 1; L.p.oy_add = 0; L.p.ox_add = 0;
+        bool yh = false;
+        if (two_sm) {
+            const int r = plan_yhalo(L.p, n_tile, split);
+            if (r) {
+                yh = true;
+                const uint32_t boxy[4] = {KCHUNK, TILE_W, (uint32_t)r, 1};
+                if ((rc = encode_map(&L.p.a_hi[0], x0_hi, 4, dims, str, boxy)) != LWB_OK) return fail(rc);
+                if (split && (rc = encode_map(&L.p.a_lo[0], x0_lo, 4, dims, str, boxy)) != LWB_OK) return fail(rc);
+            }
+        }
         finish(L, d->h_out, d->w_out);
+        L.yhalo = yh;
         *plan_out = plan;
         return LWB_OK;
     }
@@ -1500,7 +1770,17 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
         for (int t = 0; t < 4; t++) { L.p.dy[t] = (signed char)(t >> 1); L.p.dx[t] = (signed char)(t & 1); L.p.tmap[t] = 0; L.p.wtap[t] = (short)t; }
         L.p.ntaps = 4; L.p.chunks0 = d->cin0 / kc; L.p.chunks1 = 0;
         L.p.oy_mul = 2; L.p.ox_mul = 2; L.p.oy_add = 0; L.p.ox_add = 0;
+        bool yh = false;
+        if (two_sm && kc == KCHUNK) {
+            const int r = plan_yhalo(L.p, n_tile, split);
+            if (r) {
+                yh = true;
+                if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0, kc, r)) != LWB_OK) return fail(rc);
+                if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0, kc, r)) != LWB_OK) return fail(rc);
+            }
+        }
         finish(L, d->h_in, d->w_in);
+        L.yhalo = yh;
         L.p.phase_cols = d->cout;
         L.p.n_tiles_n = ncols / n_tile;
         const long total_super = (long)L.p.n_img * L.p.tiles_y * L.p.tiles_x * L.p.n_tiles_n / cl;
@@ -1541,21 +1821,6 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     LWB_CHECK_ARG(d->stride == 1 || d->cin1 == 0, "concat input only with stride 1");
     Launch& L = plan->launches[plan->num++];
     memset(&L.p, 0, sizeof(L.p));
-    if (d->stride == 1) {
-        if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0, kc)) != LWB_OK) return fail(rc);
-        if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0, kc)) != LWB_OK) return fail(rc);
-        if (d->cin1) {
-            if ((rc = map_nhwc(&L.p.a_hi[1], x1_hi, d->n, d->h_in, d->w_in, d->cin1, kc)) != LWB_OK) return fail(rc);
-            if (split && (rc = map_nhwc(&L.p.a_lo[1], x1_lo, d->n, d->h_in, d->w_in, d->cin1, kc)) != LWB_OK) return fail(rc);
-        }
-    } else {
-        for (int py = 0; py < 2; py++) for (int px = 0; px < 2; px++) {
-            if ((rc = map_nhwc_parity(&L.p.a_hi[py * 2 + px], x0_hi, d->n, d->h_in, d->w_in, d->cin0, py, px, kc)) != LWB_OK) return fail(rc);
-            if (split && (rc = map_nhwc_parity(&L.p.a_lo[py * 2 + px], x0_lo, d->n, d->h_in, d->w_in, d->cin0, py, px, kc)) != LWB_OK) return fail(rc);
-        }
-    }
-    if ((rc = encode_map(&L.p.w_hi, w_hi, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
-    if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, wd, ws, wb)) != LWB_OK) return fail(rc);
     int t = 0;
     for (int ky = 0; ky < d->kh; ky++) for (int kx = 0; kx < d->kw; kx++) {
         const int oy = ky * d->dil - d->pad, ox = kx * d->dil - (d->pad_w >= 0 ? d->pad_w : d->pad);   // input offset relative to stride*y
@@ -1573,7 +1838,34 @@ extern "C" int lwb_conv_plan_create(const lwb_conv_desc* d,
     }
     L.p.ntaps = t; L.p.chunks0 = d->cin0 / kc; L.p.chunks1 = d->cin1 / kc;
     L.p.oy_mul = 1; L.p.ox_mul = 1; L.p.oy_add = 0; L.p.ox_add = 0;
+    // y-halo schedule (k_conv_tc2y): also opens the cta_group::2 path to N = 32 (folded heads, 16-channel gated layers)
+    int rows = TILE_H;
+    bool yh = false;
+    {
+        const bool pair_ok = !d->halo && (m_tiles0 % 2 == 0) && sms >= 2 && kc == KCHUNK && want_2sm;
+        if ((two_sm || (pair_ok && n_tile == 32)) && kc == KCHUNK) {
+            const int r = plan_yhalo(L.p, n_tile, split);
+            if (r) { rows = r; yh = true; two_sm = true; cl = 2; }
+        }
+    }
+    const uint32_t wb2[3] = {(uint32_t)kc, (uint32_t)(n_tile / cl), 1};
+    if (d->stride == 1) {
+        if ((rc = map_nhwc(&L.p.a_hi[0], x0_hi, d->n, d->h_in, d->w_in, d->cin0, kc, rows)) != LWB_OK) return fail(rc);
+        if (split && (rc = map_nhwc(&L.p.a_lo[0], x0_lo, d->n, d->h_in, d->w_in, d->cin0, kc, rows)) != LWB_OK) return fail(rc);
+        if (d->cin1) {
+            if ((rc = map_nhwc(&L.p.a_hi[1], x1_hi, d->n, d->h_in, d->w_in, d->cin1, kc, rows)) != LWB_OK) return fail(rc);
+            if (split && (rc = map_nhwc(&L.p.a_lo[1], x1_lo, d->n, d->h_in, d->w_in, d->cin1, kc, rows)) != LWB_OK) return fail(rc);
+        }
+    } else {
+        for (int py = 0; py < 2; py++) for (int px = 0; px < 2; px++) {
+            if ((rc = map_nhwc_parity(&L.p.a_hi[py * 2 + px], x0_hi, d->n, d->h_in, d->w_in, d->cin0, py, px, kc, rows)) != LWB_OK) return fail(rc);
+            if (split && (rc = map_nhwc_parity(&L.p.a_lo[py * 2 + px], x0_lo, d->n, d->h_in, d->w_in, d->cin0, py, px, kc, rows)) != LWB_OK) return fail(rc);
+        }
+    }
+    if ((rc = encode_map(&L.p.w_hi, w_hi, 3, wd, ws, wb2)) != LWB_OK) return fail(rc);
+    if (split && (rc = encode_map(&L.p.w_lo, w_lo, 3, wd, ws, wb2)) != LWB_OK) return fail(rc);
     finish(L, d->h_out, d->w_out);
+    L.yhalo = yh;
     *plan_out = plan;
     return LWB_OK;
 }
