@@ -1876,8 +1876,8 @@ extern "C" int lwb_conv_plan_fuse_norm(lwb_conv_plan* plan, const lwb_fused_norm
     if (plan->num != 1) { lwb::set_error("fuse_norm: multi-launch plans (transposed convs) keep the separate norm pass"); return LWB_E_UNSUPPORTED; }
     Launch& L = plan->launches[0];
     ConvParams& p = L.p;
-    if (L.halo || !L.two_sm || !L.split || L.n_tile < 128 || !p.stats || p.oy_mul != 1 || p.ox_mul != 1) {
-        lwb::set_error("fuse_norm: needs a split-mode cta_group::2 plan with N tile >= 128 and statistics");
+    if (L.halo || L.yhalo || !L.two_sm || !L.split || L.n_tile < 128 || !p.stats || p.oy_mul != 1 || p.ox_mul != 1) {
+        lwb::set_error("fuse_norm: needs a split-mode cta_group::2 plan (not the y-halo variant) with N tile >= 128 and statistics");
         return LWB_E_UNSUPPORTED;
     }
     const int tiles_per_image = p.tiles_y * p.tiles_x;
