@@ -86,7 +86,7 @@ struct ConvParams {
     // dy are consecutive; the group's activation tile (TILE_H + cnt - 1 rows) is fetched ONCE and tap i reads it i rows down
     int ngroups; unsigned char g_first[MAX_TAPS], g_cnt[MAX_TAPS];
     int a_rows;                       // rows of the activation box = TILE_H + max group size - 1
-    int nb_stages;                    // weight ring depth
+    int na_stages, nb_stages;         // activation / weight ring depths
     int phase_cols;                   // > 0: merged transposed conv -- column block col / phase_cols = sub-pixel phase (a, b) =
                                       // (ph >> 1, ph & 1) of output pixel (2y + a, 2x + b), channel = col % phase_cols
 };
@@ -896,10 +896,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2(const __grid_consta
 // SWIZZLE_128B atom: a tile of TILE_H + cnt - 1 rows fetched once serves all cnt taps of the group through the UMMA
 // descriptor's start address (+ i * 1024 B; the swizzle phase lives in address bits 7-9 and does not change).  For a 3x3
 // filter the activation fill drops to 18/48 of its bytes, for the 7-tap heads / stem to 22/112.
-//   A ring: NA = 2 entries of a_rows KB (x2 with lo);  full[s] in the leader (both CTAs' bytes), empty[s] per CTA
-//   B ring: nb_stages entries of N/2 weight rows (x2 with lo), one entry per tap
+//   A ring: na_stages (2-4) entries of a_rows KB (x2 with lo);  full[s] in the leader (both CTAs' bytes), empty[s] per CTA
+//   B ring: nb_stages (3-8) entries of N/2 weight rows (x2 with lo), one entry per tap
+// (an activation entry now lasts cnt taps of MMA time, so the ring is as deep as shared memory allows: 2 entries at N = 256,
+// 3-4 for the narrow layers, where two entries could not cover the TMA latency)
 // =====================================================================================================
-constexpr int Y_NA = 2;
+constexpr int Y_MAX_NA = 4;
 constexpr int Y_MAX_NB = 8;
 
 template <int N_TILE, bool SPLIT>
@@ -920,11 +922,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2y(const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_plane = P.a_rows * 1024;                        // one of hi / lo
     const int a_stage = a_plane * (SPLIT ? 2 : 1);
+    const int na = P.na_stages;
     uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + Y_NA * a_stage;
+    uint8_t* b_ring = smem + na * a_stage;
     uint64_t* bar_afull = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
-    uint64_t* bar_aempty = bar_afull + Y_NA;
-    uint64_t* bar_bfull = bar_aempty + Y_NA;
+    uint64_t* bar_aempty = bar_afull + Y_MAX_NA;
+    uint64_t* bar_bfull = bar_aempty + Y_MAX_NA;
     uint64_t* bar_bempty = bar_bfull + Y_MAX_NB;
     uint64_t* bar_tfull = bar_bempty + Y_MAX_NB;
     uint64_t* bar_tempty = bar_tfull + 2;
@@ -939,7 +942,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2y(const __grid_const
 
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < Y_NA; s++) { mbar_init(bar_afull + s, 1); mbar_init(bar_aempty + s, 1); }
+            for (int s = 0; s < Y_MAX_NA; s++) { mbar_init(bar_afull + s, 1); mbar_init(bar_aempty + s, 1); }
             for (int s = 0; s < Y_MAX_NB; s++) { mbar_init(bar_bfull + s, 1); mbar_init(bar_bempty + s, 1); }
             for (int b = 0; b < 2; b++) { mbar_init(bar_tfull + b, 1); mbar_init(bar_tempty + b, 8); }
             fence_barrier_init();
@@ -988,7 +991,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2y(const __grid_const
                         if (SPLIT) tma_load_4d_2sm(&P.a_lo[mi], sta + a_plane, afullc, c0, x0 + P.dx[t0], y0 + P.dy[t0], img);
                     }
                     __syncwarp();
-                    if (++sa == Y_NA) { sa = 0; pa ^= 1; }
+                    if (++sa == na) { sa = 0; pa ^= 1; }
                     for (int i = 0; i < cnt; i++) {
                         mbar_wait(bar_bempty + sb, pb ^ 1);
                         uint8_t* stb = b_ring + sb * C::B_STAGE;
@@ -1051,7 +1054,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv_tc2y(const __grid_const
                         }
                         if (elect_one()) umma_commit_2sm(bar_aempty + sa, 3);   // activation slot free in BOTH CTAs
                         __syncwarp();
-                        if (++sa == Y_NA) { sa = 0; pa ^= 1; }
+                        if (++sa == na) { sa = 0; pa ^= 1; }
                     }
                 }
                 if (elect_one()) umma_commit_2sm(bar_tfull + abuf, 3);
@@ -1482,8 +1485,8 @@ int launch(const Launch& L, cudaStream_t st)
 // (disabled, longest run 1, rings do not fit).
 int plan_yhalo(ConvParams& p, int n_tile, bool split)
 {
-    static int want = -1;
-    if (want < 0) { const char* e = getenv("LWB_YHALO"); want = e ? atoi(e) : 1; }
+    const char* e = getenv("LWB_YHALO");                     // read per plan: tests switch it between plans
+    const int want = e ? atoi(e) : 1;
     if (!want || p.ntaps < 2) return 0;
     int order[MAX_TAPS];
     for (int t = 0; t < p.ntaps; t++) order[t] = t;
@@ -1507,12 +1510,17 @@ int plan_yhalo(ConvParams& p, int n_tile, bool split)
     const int a_rows = TILE_H + maxcnt - 1;
     const int a_stage = a_rows * 1024 * (split ? 2 : 1);
     const int b_stage = (n_tile / 2) * 128 * (split ? 2 : 1);
-    int nb = (196 * 1024 - Y_NA * a_stage) / b_stage;
+    int na = 0, nb = 0;
+    for (int cand = Y_MAX_NA; cand >= 2 && !na; cand--) {    // deepest activation ring that leaves a useful weight ring
+        const int left = (196 * 1024 - cand * a_stage) / b_stage;
+        if (left >= (cand == 2 ? 3 : 4)) { na = cand; nb = left; }
+    }
+    if (!na) return 0;
     if (nb > Y_MAX_NB) nb = Y_MAX_NB;
-    if (nb < 3) return 0;
+    { const char* f = getenv("LWB_YHALO_NA"); if (f && atoi(f) >= 2 && atoi(f) <= na) { na = atoi(f); nb = (196 * 1024 - na * a_stage) / b_stage; if (nb > Y_MAX_NB) nb = Y_MAX_NB; } }
     for (int i = 0; i < p.ntaps; i++) { p.dy[i] = dy[i]; p.dx[i] = dx[i]; p.tmap[i] = tm[i]; p.wtap[i] = wt[i]; }
     for (int g = 0; g < ng; g++) { p.g_first[g] = first[g]; p.g_cnt[g] = cnt[g]; }
-    p.ngroups = ng; p.a_rows = a_rows; p.nb_stages = nb;
+    p.ngroups = ng; p.a_rows = a_rows; p.na_stages = na; p.nb_stages = nb;
     return a_rows;
 }
 

@@ -360,9 +360,10 @@ def test_conv_7x1_folded_heads(cuda, split):
 
 @pytest.mark.parametrize("variant", ["plain", "res_warp"])
 @pytest.mark.parametrize("split", [1, 2])
-def test_conv_fused_instance_norm(cuda, split, variant):
+def test_conv_fused_instance_norm(cuda, split, variant, monkeypatch):
     """lwb_conv_plan_fuse_norm against conv + lwb_norm_act_nhwc on the same operands: 512 -> 512 @32x32, batch 3 (24 tiles per
     N tile: several CTAs wait on every unit), twice in a row (counters / statistics re-zeroed)."""
+    monkeypatch.setenv("LWB_YHALO", "0")                  # the fused epilogue lives in the non-halo 2-CTA kernel
     n, c, h, w = 3, 512, 32, 32
     x = rnd(n, c, h, w, seed=41)
     wt = rnd(c, c, 3, 3, seed=42, scale=0.03)

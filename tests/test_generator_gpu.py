@@ -214,6 +214,7 @@ def test_fused_instance_norm_matches_separate_pass(cuda, net, monkeypatch, mode)
     n, sd = net
     monkeypatch.setenv("LWB_PRECISION", mode)
     monkeypatch.setenv("LWB_STREAMS", "1")                   # the fused kernels' CTAs wait on each other: single stream only
+    monkeypatch.setenv("LWB_YHALO", "0")                     # ... and the fused epilogue lives in the non-halo 2-CTA kernel
     inp = S.synthetic_generator_inputs(3, 256, seed=44)
     src, tsf, T = inp["src"].to(cuda), inp["tsf"].to(cuda), inp["T"].to(cuda)
     monkeypatch.setenv("LWB_FUSE_NORM", "0")

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_conv_gpu.py -m gpu -q -x -p no:cacheprovider --timeout 600 > gpurun_out/pytest_yhalo_conv.log 2>&1; echo "conv tests (yhalo on) rc=$?"; tail -15 gpurun_out/pytest_yhalo_conv.log
 timeout 900 python -m pytest tests/test_generator_gpu.py tests/test_hmr_gpu.py tests/test_inpaintor.py -m gpu -q -x -p no:cacheprovider --timeout 600 > gpurun_out/pytest_yhalo_gen.log 2>&1; echo "generator/hmr/inpaintor tests (yhalo on) rc=$?"; tail -8 gpurun_out/pytest_yhalo_gen.log
-for v in "LWB_YHALO=1" "LWB_YHALO=0"; do
+for v in "LWB_YHALO=1" "LWB_YHALO_NA=2" "LWB_YHALO=0"; do
   timeout 400 env $v python bench.py --steps 20 --warmup 5 --no-cpu-baseline --steady-steps 100 > gpurun_out/y_$v.json 2> gpurun_out/y_$v.err; echo "bench $v rc=$?"; tail -2 gpurun_out/y_$v.err
   python - "gpurun_out/y_$v.json" <<'PY'
 import json, sys
