@@ -49,6 +49,17 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction instead of two
+// 16-byte halves -- half the L1/L2 transactions of the fp32 activation streams.  Addresses must be 32-byte aligned.
+__device__ __forceinline__ void ldg_f32x8(const float* p, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg_f32x8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): the 2-term operand split of the conv engine.
 __device__ __forceinline__ void split_half(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);

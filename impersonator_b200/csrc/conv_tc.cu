@@ -316,16 +316,15 @@ __device__ __forceinline__ void epilogue_loop(const PT& P, int warp, unsigned la
                 for (int j = 0; j < CW; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * P.out_scale);
             }
             if (valid && P.out) {
-                float4* o = reinterpret_cast<float4*>(optr + c * CW);
+                float* o = optr + c * CW;
                 if (P.phase_cols > 0) {
                     const int col = n_idx * N_TILE + c * CW, ph = col / P.phase_cols;
-                    o = reinterpret_cast<float4*>(P.out + (((size_t)img * P.out_h + 2 * y) * P.out_w + 2 * x) * P.cout
-                                                  + (size_t)(ph >> 1) * out_w_c + (ph & 1) * P.cout + (col - ph * P.phase_cols));
+                    o = P.out + (((size_t)img * P.out_h + 2 * y) * P.out_w + 2 * x) * P.cout
+                      + (size_t)(ph >> 1) * out_w_c + (ph & 1) * P.cout + (col - ph * P.phase_cols);
                 }
+                // 32 bytes (one full sector) per store: rows of a warp are different pixels, so nothing coalesces across lanes
 #pragma unroll
-                for (int j = 0; j < CW / 4; j++)
-                    o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                for (int j = 0; j < CW / 8; j++) lwb::stg_f32x8(o + 8 * j, reinterpret_cast<const float*>(r + 8 * j));
             }
             if (P.stats) {
                 float v[CW], v2[CW];

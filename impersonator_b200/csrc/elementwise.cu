@@ -264,9 +264,11 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
         ok[r] = pg < npix;
         bb[r] = ok[r] ? (int)(pg / hw) : 0;
         off[r] = (size_t)(ok[r] ? pg : 0) * P.c + g * 8;
-        const float4* src = reinterpret_cast<const float4*>(P.raw + off[r]);
-        const float4 a = ok[r] ? __ldg(src) : make_float4(0, 0, 0, 0), c = ok[r] ? __ldg(src + 1) : make_float4(0, 0, 0, 0);
-        v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w; v[r][4] = c.x; v[r][5] = c.y; v[r][6] = c.z; v[r][7] = c.w;
+        if (ok[r]) lwb::ldg_f32x8(P.raw + off[r], v[r]);             // one 32-byte sector per lane (LDG.256)
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[r][k] = 0.f;
+        }
     }
     float res[R][8];
     if (P.residual) {
@@ -277,9 +279,11 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
                 const int pix = (int)((pix0 + r * ppb + lp) % hw), y = pix / P.w, x = pix % P.w, st = P.res_step;
                 roff = (((size_t)bb[r] * (P.h * st) + (size_t)y * st) * (P.w * st) + (size_t)x * st) * P.c + g * 8;
             }
-            const float4* src = reinterpret_cast<const float4*>(P.residual + roff);
-            const float4 a = ok[r] ? __ldg(src) : make_float4(0, 0, 0, 0), c = ok[r] ? __ldg(src + 1) : make_float4(0, 0, 0, 0);
-            res[r][0] = a.x; res[r][1] = a.y; res[r][2] = a.z; res[r][3] = a.w; res[r][4] = c.x; res[r][5] = c.y; res[r][6] = c.z; res[r][7] = c.w;
+            if (ok[r]) lwb::ldg_f32x8(P.residual + roff, res[r]);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) res[r][k] = 0.f;
+            }
         }
     }
 #pragma unroll
@@ -310,21 +314,17 @@ __global__ void __launch_bounds__(256, 4) k_norm_act(NormActParams P)
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 if (tp.m & (1 << t)) {
-                    const float4* q = reinterpret_cast<const float4*>(src + (size_t)offs[t] * P.c);
-                    const float4 a = __ldg(q), c = __ldg(q + 1);
-                    acc[0] += a.x * wt[t]; acc[1] += a.y * wt[t]; acc[2] += a.z * wt[t]; acc[3] += a.w * wt[t];
-                    acc[4] += c.x * wt[t]; acc[5] += c.y * wt[t]; acc[6] += c.z * wt[t]; acc[7] += c.w * wt[t];
+                    float q[8];
+                    lwb::ldg_f32x8(src + (size_t)offs[t] * P.c, q);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[k] += q[k] * wt[t];
                 }
             }
 #pragma unroll
             for (int k = 0; k < 8; k++) v[r][k] += acc[k];
         }
         if (!ok[r]) continue;
-        if (P.y_f32) {
-            float4* o = reinterpret_cast<float4*>(P.y_f32 + off[r]);
-            o[0] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-            o[1] = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
-        }
+        if (P.y_f32) lwb::stg_f32x8(P.y_f32 + off[r], v[r]);
         if (P.y_hi) {
             if (EXT && P.post_scale) {
                 const float4* ps = reinterpret_cast<const float4*>(P.post_scale + g * 8);
