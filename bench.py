@@ -207,6 +207,10 @@ def workload_config(args, frames_per_step=None):
             "image_size": args.size, "precision": "LWB_PRECISION=%s: fp16 hi/lo operand split on tcgen05, fp32 accumulate (parity-gated 1e-3 vs fp32)"
                          % os.environ.get("LWB_PRECISION", "fp16f8 (default)"),
             "parallelism": "frames sharded, dp%d, no per-step collective" % args.gpus,
+            "engine": {k: os.environ.get(k, d) for k, d in (("LWB_STREAMS", "2 (default)"), ("LWB_GRAPH", "1 (default)"),
+                                                              ("LWB_YHALO", "1 (default)"), ("LWB_TC_HEADS", "1 (default)"),
+                                                              ("LWB_CONVT_MERGE", "1 (default)"), ("LWB_FUSE_NORM", "0 (default)"),
+                                                              ("LWB_ALIGN_CORNERS", "1 (default, torch-1.2 grid_sample)"))},
             "l2": "per-step working set (~2 GB of activations at batch 16) >> 126 MB L2; inputs rotate over 4 frame sets"}
 
 

@@ -41,11 +41,11 @@ def precision_mode():
 
 
 def _sub_batches(B, enc_w, res_w, bg):
-    """LWB_STREAMS (default 2, at most 4): number of concurrent sub-batches ImpersonatorGenerator.inference splits a batch
+    """LWB_STREAMS (default 2, at most 2): number of concurrent sub-batches ImpersonatorGenerator.inference splits a batch
     into.  Only when the source features / background are shared by the batch (the imitation case), B divides evenly and
     every sub-batch keeps at least 4 frames."""
     try:
-        n = min(4, int(os.environ.get("LWB_STREAMS", "2")))        # measured on B200: 2 sub-batches +6 % (default)
+        n = min(2, int(os.environ.get("LWB_STREAMS", "2")))        # measured on B200: 2 sub-batches +6 %; 4 hung the bench (not pursued)
     except ValueError:
         n = 1
     if n <= 1 or B % n or B // n < 4:
