@@ -20,12 +20,14 @@ cap() {  # name, kernel regex, skip, count
 }
 # DRAM traffic of every conv launch of one step (roofline.traffic): cheap metrics pass
 timeout 600 env LWB_STREAMS=1 LWB_GRAPH=0 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:k_conv_tc -c 64 --csv --log-file gpurun_out/conv_traffic.csv $BENCH > gpurun_out/ncu_traffic.log 2>&1; echo "traffic rc=$?"
-# k_conv_tc2 launches of one step, in order: stem, 3 encoders, 12 residual convs, 4 phase launches of T512->256, skipper @64,
-# merged T256->128, skipper @128, merged T128->64, skipper @256 (index 24); the folded heads are the only k_conv_tc launch
-cap conv_res "^k_conv_tc2$" 8 2
-cap conv_convt_merged "^k_conv_tc2$" 23 1
-cap conv_skip256 "^k_conv_tc2$" 24 1
-cap conv_heads "^k_conv_tc$" 0 1
+# k_conv_tc2y (y-halo, default) launches of one step, in order: 0 stem, 1-3 encoders, 4-15 residual convs, 16 skipper @64,
+# 17 merged T256->128, 18 skipper @128, 19 merged T128->64, 20 skipper @256, 21 folded heads (N = 32); the four phase launches
+# of T512->256 are the only k_conv_tc2 (non-halo) launches
+cap conv_res "^k_conv_tc2y$" 8 2
+cap conv_stem "^k_conv_tc2y$" 0 1
+cap conv_convt_merged "^k_conv_tc2y$" 19 1
+cap conv_skip256 "^k_conv_tc2y$" 20 1
+cap conv_heads "^k_conv_tc2y$" 21 1
 cap norm "k_norm_act" 0 2
 cap heads "k_heads" 0 1
 cap raster "k_face_raster|k_resolve" 0 2
