@@ -28,6 +28,7 @@
 namespace {
 
 constexpr int   kSmallBox   = 48;       // boxes up to this many pixels are walked by one thread
+constexpr int   kBigBox     = 2048;     // boxes beyond this are walked by the whole grid (k_face_whole), not by one warp
 constexpr float kSliverTol  = 1e-5f;
 constexpr float kBoxMargin  = 0.02f;    // pixels added around the exact bounding box    // |det| / (longest edge)^2 below this -> whole-image scan
 
@@ -159,6 +160,24 @@ __device__ __forceinline__ void test_pixel(const RasterParams& P, const float* f
     }
 }
 
+// Conservative pixel box of a non-degenerate face (see k_face_raster), or whole = true when the reference's inside test is not
+// confined to the box (degenerate / sliver / non-finite faces).
+__device__ __forceinline__ void face_box(const float* p, float det, int is, bool& whole, int& bx0, int& bx1, int& by0, int& by1)
+{
+    const float xmin = fminf(p[0], fminf(p[2], p[4])), xmax = fmaxf(p[0], fmaxf(p[2], p[4]));
+    const float ymin = fminf(p[1], fminf(p[3], p[5])), ymax = fmaxf(p[1], fmaxf(p[3], p[5]));
+    const float ex = fmaxf(xmax - xmin, ymax - ymin);
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < 6; k++) finite = finite && (fabsf(p[k]) < 1e30f);    // false for NaN / inf
+    whole = !finite || !(fabsf(det) > kSliverTol * ex * ex);
+    bx0 = by0 = 0; bx1 = by1 = -1;
+    if (!whole) {
+        bx0 = max(0, (int)ceilf(xmin - kBoxMargin)); bx1 = min(is - 1, (int)floorf(xmax + kBoxMargin));
+        by0 = max(0, (int)ceilf(ymin - kBoxMargin)); by1 = min(is - 1, (int)floorf(ymax + kBoxMargin));
+    }
+}
+
 template <bool FROM_VERTS>
 __global__ void __launch_bounds__(256) k_face_raster(RasterParams P)
 {
@@ -186,29 +205,21 @@ __global__ void __launch_bounds__(256) k_face_raster(RasterParams P)
 #pragma unroll
                 for (int k = 0; k < 9; k++) o[k] = inv[k];
             }
-            const float xmin = fminf(p[0], fminf(p[2], p[4])), xmax = fmaxf(p[0], fmaxf(p[2], p[4]));
-            const float ymin = fminf(p[1], fminf(p[3], p[5])), ymax = fmaxf(p[1], fmaxf(p[3], p[5]));
-            const float ex = fmaxf(xmax - xmin, ymax - ymin);
-            bool finite = true;
-#pragma unroll
-            for (int k = 0; k < 6; k++) finite = finite && (fabsf(p[k]) < 1e30f);    // false for NaN / inf
             // Degenerate or sliver triangles: the reference's inside test is then not confined to the
             // bounding box (all three edge products can round to equality), so scan the whole image
-            // exactly like the reference does.
-            const bool whole = !finite || !(fabsf(det) > kSliverTol * ex * ex);
-            if (whole) {
-                // deferred to k_face_whole, where the whole grid shares the 65k-pixel scan of each such face
-                // (one warp walking a full image would straggle for ~1 ms)
+            // exactly like the reference does.  Conservative box otherwise, in pixel-centre coordinates (pixel i has
+            // p-coordinate exactly i): for a non-sliver triangle a rounding-induced false accept of the reference's edge
+            // tests lies within ~1e-6 NDC (< 1e-3 px up to 2048^2) of the triangle; kBoxMargin absorbs that.
+            bool whole;
+            face_box(p, det, P.is, whole, bx0, bx1, by0, by1);
+            const int area = whole ? 0 : max(0, bx1 - bx0 + 1) * max(0, by1 - by0 + 1);
+            if (whole || area > kBigBox) {
+                // deferred to k_face_whole, where the whole grid shares the scan of each such face (one warp walking a full
+                // image -- or a face covering thousands of pixels -- would straggle for up to ~1 ms)
                 const unsigned slot = atomicAdd(P.qcount, 1u) + 1u;          // counter starts at 0xFFFFFFFF
                 P.queue[slot] = (unsigned)gid;
-            } else {
-                // Conservative box in pixel-centre coordinates (pixel i has p-coordinate exactly i).  For a
-                // non-sliver triangle a rounding-induced false accept of the reference's edge tests lies
-                // within ~1e-6 NDC (< 1e-3 px up to 2048^2) of the triangle; kBoxMargin absorbs that.
-                bx0 = max(0, (int)ceilf(xmin - kBoxMargin)); bx1 = min(P.is - 1, (int)floorf(xmax + kBoxMargin));
-                by0 = max(0, (int)ceilf(ymin - kBoxMargin)); by1 = min(P.is - 1, (int)floorf(ymax + kBoxMargin));
-                if (bx0 <= bx1 && by0 <= by1)
-                    mode = ((bx1 - bx0 + 1) * (by1 - by0 + 1) <= kSmallBox) ? 1 : 2;
+            } else if (area > 0) {
+                mode = (area <= kSmallBox) ? 1 : 2;
             }
         }
     }
@@ -235,7 +246,8 @@ __global__ void __launch_bounds__(256) k_face_raster(RasterParams P)
 
 // Faces whose inside test is not confined to their bounding box (degenerate / sliver / non-finite):
 // the reference effectively tests them against every pixel, and so does this kernel -- spread over the
-// whole grid: blockIdx.y strides over the queued faces, blockIdx.x over pixel chunks.
+// whole grid: blockIdx.y strides over the queued faces, blockIdx.x over pixel chunks.  Ordinary faces with a box of more
+// than kBigBox pixels are queued here too and scanned over their box only.
 template <bool FROM_VERTS>
 __global__ void __launch_bounds__(256) k_face_whole(RasterParams P)
 {
@@ -247,8 +259,17 @@ __global__ void __launch_bounds__(256) k_face_whole(RasterParams P)
         float f[9], p[6], inv[9], det;
         load_face<FROM_VERTS>(P, b, fn, f);
         face_setup(f, P.is, p, inv, det);
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x)
-            test_pixel(P, f, inv, b, fn, i % P.is, i / P.is);
+        bool whole;
+        int bx0, bx1, by0, by1;
+        face_box(p, det, P.is, whole, bx0, bx1, by0, by1);
+        if (whole) {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x)
+                test_pixel(P, f, inv, b, fn, i % P.is, i / P.is);
+        } else {                                             // a big ordinary face: only its box, spread over the x-blocks
+            const int bw = bx1 - bx0 + 1, n = bw * (by1 - by0 + 1);
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+                test_pixel(P, f, inv, b, fn, bx0 + i % bw, by0 + i / bw);
+        }
     }
 }
 

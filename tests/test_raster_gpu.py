@@ -106,6 +106,31 @@ def test_random_triangle_soup_bit_exact(cuda):
         compare_with_gpu_ref(random_soup(2, 3000, seed).to(cuda), size)
 
 
+def test_big_faces_bit_exact_and_grid_wide(cuda):
+    """Many faces covering thousands of pixels each (boxes > kBigBox go to the grid-wide scan instead of one warp): bit-exact
+    against the reference kernels, and not a straggler."""
+    g = torch.Generator().manual_seed(11)
+    B, F = 2, 1500
+    c = torch.rand(B, F, 1, 2, generator=g) * 1.6 - 0.8
+    size = 0.2 + torch.rand(B, F, 1, 1, generator=g) * 1.2                 # 25..180 px wide at 256^2
+    xy = c + (torch.rand(B, F, 3, 2, generator=g) - 0.5) * size
+    z = 1.0 + torch.rand(B, F, 3, 1, generator=g) * 3
+    faces = torch.cat([xy, z], dim=-1).float().contiguous().to(cuda)
+    compare_with_gpu_ref(faces, 256)
+    for _ in range(3):
+        run_mine(faces, 256, want_inv=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        run_mine(faces, 256, want_inv=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print("3000 large faces (avg box ~10^4 px) @256^2: %.3f ms" % ms)
+    assert ms < 5.0
+
+
 def test_flip_rows_matches_torch_flip(cuda):
     faces, _, _, _ = sphere_faces(2, 5, cuda)
     a = run_mine(faces, 256, flip=False, want_inv=False)
