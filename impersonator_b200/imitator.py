@@ -456,15 +456,21 @@ class Imitator(object):
             self.tsf_info['image'] = last_image[0]
         if range_bits[0] and not getattr(self, '_range_retry', False):
             # Never silently: activations left the range in which the default fp16f8 operand split keeps its precision
-            # (|x| >= 1024: the e4m3 correction terms clip).  Pin the generator to fp16x3 (fp16 corrections, range 6e4)
-            # and redo the call; beyond the fp16 range nothing in this engine can represent the activations.
+            # (bit 0: |x| >= 1024, the e4m3 correction terms clip; bit 2: output-head pre-activations of +-8 and more, where
+            # its ~1e-4 relative precision may exceed 1e-3 on pixels).  Pin the generator to fp16x3 (fp16 corrections, range
+            # 6e4) and redo the call -- LWB_AUTO_PRECISION=0 only warns; beyond the fp16 range (bit 1) nothing in this
+            # engine can represent the activations.
             import warnings
             if range_bits[0] & 2:
                 raise LwbError("generator activations exceed the fp16 range (|x| >= 6e4 or non-finite): the conv engine's "
                                "fp16 operands cannot represent them")
-            warnings.warn("lwb_b200: %s; switching this generator to LWB_PRECISION=fp16x3 and recomputing the sequence"
-                          % ("activations beyond the fp16f8 correction range (|x| >= 1024)" if range_bits[0] & 1 else
-                             "output-head pre-activations beyond +-8 (fp16f8's ~1e-4 relative precision would exceed 1e-3 on pixels)"))
+            what = ("activations beyond the fp16f8 correction range (|x| >= 1024)" if range_bits[0] & 1 else
+                    "output-head pre-activations beyond +-8 (fp16f8's ~1e-4 relative precision may exceed 1e-3 on pixels)")
+            if os.environ.get("LWB_AUTO_PRECISION", "1") == "0" or getattr(self.generator, '_lwb_precision', None) == "fp16x3" \
+                    or os.environ.get("LWB_PRECISION", "fp16f8") != "fp16f8":
+                warnings.warn("lwb_b200: %s (precision mode kept)" % what)
+                return outputs
+            warnings.warn("lwb_b200: %s; switching this generator to LWB_PRECISION=fp16x3 and recomputing the sequence" % what)
             self.generator.set_precision("fp16x3")
             self._range_retry = True
             try:
@@ -526,10 +532,13 @@ class SyntheticBodyModel(object):
 
     def __init__(self, base_verts):
         self.base = base_verts
+        self._on = {}
 
     def get_details(self, theta):
         dev = theta.device
-        base = self.base.to(dev)
+        if dev not in self._on:                          # one upload per device (a per-call H2D copy cannot be graph-captured)
+            self._on[dev] = self.base.to(dev)
+        base = self._on[dev]
         cam = theta[:, 0:3].contiguous()
         ry, rx = theta[:, 3], theta[:, 4]
         cy, sy, cx, sx = torch.cos(ry), torch.sin(ry), torch.cos(rx), torch.sin(rx)
