@@ -29,11 +29,21 @@ import os
 import torch
 import torch.nn as nn
 
+from . import graph as _graph
 from . import kernels as K
 from ._lib import LwbError
 
 
 DEFAULT_PRECISION = "fp16f8"
+
+
+_WEIGHTS_EPOCH = [0]
+
+
+def weights_epoch():
+    """Bumped whenever a network's parameters may have changed (load_state_dict, init_weights, .to()/.half()...): packed
+    weights and per-shape streams are rebuilt then, and anything that cached launches against them must be rebuilt too."""
+    return _WEIGHTS_EPOCH[0]
 
 
 def precision_mode():
@@ -156,6 +166,7 @@ class NetworkBase(nn.Module):
             m.bias.data.fill_(0)
 
     def _lwb_invalidate(self):
+        _WEIGHTS_EPOCH[0] += 1                               # captured graphs keyed on it (imitator._chunk_step) are re-captured
         for m in self.modules():
             if hasattr(m, '_lwb_streams'):
                 m._lwb_streams = {}
@@ -594,7 +605,7 @@ def _stream_for(mod, cls, key, *args, **kw):
         while len(streams) >= 8:                         # evict the least recently used shape only (each holds ~GBs at B=16)
             streams.pop(next(iter(streams)))
         streams[key] = cls(mod, *args, **kw)
-    return streams[key]
+    return _graph.pin(streams[key])                      # a CUDA graph being captured keeps what it replays into alive
 
 
 def _nhwc_of(t):

@@ -16,6 +16,18 @@ import torch
 from . import kernels as K
 
 
+_OPEN = []                                                       # pin lists of the CapturedStep objects being built
+
+
+def pin(obj):
+    """Called by the per-shape stream caches (generator._stream_for, ...) for every buffer-owning object they hand out: while
+    a CapturedStep is warming up / capturing, the object is also referenced by that step, so that a later LRU eviction from
+    the cache cannot free buffers, plans or TMA descriptors the captured graph still replays into."""
+    for keep in _OPEN:
+        keep.append(obj)
+    return obj
+
+
 def graphs_enabled():
     """LWB_GRAPH (default 1): replay the per-chunk launch sequence as a CUDA graph where the caller supports it."""
     return os.environ.get("LWB_GRAPH", "1") != "0"
@@ -37,6 +49,15 @@ class CapturedStep(object):
         self.graph = None
         self.static_out = None
         self.launches = 0
+        self.pinned = []                                         # stream objects (buffers, plans) the graph replays into
+        _OPEN.append(self.pinned)
+        try:
+            self._build(fn, warmup)
+        finally:
+            _OPEN.pop()
+        self.pinned[:] = list({id(o): o for o in self.pinned}.values())
+
+    def _build(self, fn, warmup):
         dev = next(v.device for v in self.static_in.values() if torch.is_tensor(v))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

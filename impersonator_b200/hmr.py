@@ -276,7 +276,8 @@ class HumanModelRecovery(nn.Module):
             while len(streams) >= 2:
                 streams.pop(next(iter(streams)))
             streams[key] = _HmrStream(self, B, inputs.device, split)
-        return streams[key].run(inputs)
+        from . import graph as _graph
+        return _graph.pin(streams[key]).run(inputs)
 
     def get_details(self, theta):
         cam = theta[:, 0:3].contiguous()

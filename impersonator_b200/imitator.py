@@ -28,7 +28,7 @@ import torch
 
 from . import kernels as K
 from ._lib import LwbError
-from .generator import ImpersonatorGenerator
+from .generator import ImpersonatorGenerator, weights_epoch
 from .nmr import SMPLRenderer
 
 
@@ -312,7 +312,7 @@ class Imitator(object):
             return self._chunk_pure(smpl, cam_strategy, hwc, u8)
         graphs = self.__dict__.setdefault('_graphs', {})
         key = (B, cam_strategy, bool(hwc), bool(u8), id(self.src_info), os.environ.get("LWB_PRECISION"),
-               os.environ.get("LWB_STREAMS"), self._ac, getattr(self.generator, '_lwb_precision', None))
+               os.environ.get("LWB_STREAMS"), self._ac, getattr(self.generator, '_lwb_precision', None), weights_epoch())
         step = graphs.get(key)
         if step is None:
             if len(graphs) >= 4:

@@ -190,7 +190,8 @@ class InpaintSANet(torch.nn.Module):
             while len(streams) >= 2:
                 streams.pop(next(iter(streams)))
             streams[key] = _InpaintStream(self, B, H, W, x.device, split)
-        return streams[key]
+        from . import graph as _graph
+        return _graph.pin(streams[key])
 
     @torch.no_grad()
     def forward(self, imgs, masks, only_out=False, only_x=False):

@@ -243,3 +243,29 @@ def test_fused_instance_norm_matches_separate_pass(cuda, net, monkeypatch, mode)
     img, mask = n.inference(enc, res, inp2["tsf"].to(cuda), inp2["T"].to(cuda))
     assert np.abs(sl(img) - g["inf_tsf_img"]).max() < TOL and np.abs(sl(mask) - g["inf_tsf_mask"]).max() < TOL
     n._lwb_invalidate()
+
+
+def test_captured_graph_survives_stream_cache_eviction(cuda, net):
+    """A captured step replays into the buffers of the per-shape stream it was recorded with.  Nine other batch sizes push
+    that shape out of the 8-entry stream cache; the graph must still own its buffers (graph.pin) and reproduce the eager
+    result bit for bit."""
+    from impersonator_b200.graph import CapturedStep
+    n, _ = net
+    size = 128
+    inp = S.synthetic_generator_inputs(3, size, seed=31)
+    enc, res = n.encode_src(inp["src"][:1].to(cuda))
+    tsf, T = inp["tsf"].to(cuda), inp["T"].to(cuda)
+    want_img, want_mask = [t.clone() for t in n.inference(enc, res, tsf, T)]
+
+    step = CapturedStep(lambda tsf, T: n.inference(enc, res, tsf, T), dict(tsf=tsf, T=T))
+    assert step.captured and step.pinned
+    for B in (1, 2, 4, 5, 6, 7, 9, 10, 11):
+        other = S.synthetic_generator_inputs(B, size, seed=40 + B)
+        n.inference(enc, res, other["tsf"].to(cuda), other["T"].to(cuda))
+    keys = [k for k in n.tsf_model._lwb_streams if k[1] == 3]
+    assert not keys, "the B=3 stream should have been evicted: %r" % (keys,)
+    junk = [torch.full((64, 1024, 1024), 7.0, device=cuda) for _ in range(4)]     # would land in freed buffers
+    img, mask = step(tsf=tsf, T=T)
+    torch.cuda.synchronize()
+    assert torch.equal(img, want_img) and torch.equal(mask, want_mask)
+    del junk

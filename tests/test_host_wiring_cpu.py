@@ -72,3 +72,36 @@ def test_inpaintor_stream_matches_oracle(monkeypatch):
     c_o, x_o, _ = R.forward(img, mask, sd)
     d = max((coarse - c_o).abs().max().item(), (x - x_o).abs().max().item())
     assert d < 2e-4, d
+
+
+def test_captured_step_pins_evicted_streams_and_epoch_bumps():
+    """A CUDA graph replays into the buffers of the per-shape streams it was captured with: the LRU cache may evict them,
+    the capturing step must keep them alive (graph.pin), and a parameter reload must change the graph key."""
+    from impersonator_b200 import generator as G, graph
+
+    class Holder(object):
+        pass
+
+    class FakeStream(object):
+        def __init__(self, mod, tag):
+            self.tag = tag
+
+    mod = Holder()
+    keep = []
+    graph._OPEN.append(keep)
+    try:
+        first = G._stream_for(mod, FakeStream, ('a',), 'a')
+        assert G._stream_for(mod, FakeStream, ('a',), 'a') is first
+    finally:
+        graph._OPEN.pop()
+    assert keep and all(o is first for o in keep)
+    for i in range(12):                                           # push 'a' out of the cache
+        G._stream_for(mod, FakeStream, ('k', i), i)
+    assert ('a',) not in mod._lwb_streams and len(mod._lwb_streams) <= 8
+    assert keep[0] is first and first.tag == 'a'                  # still referenced by the (fake) captured step
+    assert G._stream_for(mod, FakeStream, ('a',), 'a') is not first
+
+    e0 = G.weights_epoch()
+    net = G.ResNetGenerator(conv_dim=8, c_dim=4, repeat_num=1, k_size=3, n_down=1)
+    net.load_state_dict(net.state_dict())
+    assert G.weights_epoch() > e0
