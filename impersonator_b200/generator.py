@@ -782,7 +782,9 @@ class ImpersonatorGenerator(NetworkBase):
         return src_img, src_mask, tsf_img, tsf_mask
 
     @torch.no_grad()
-    def swap(self, tsf_inputs, src_encoder_outs12, src_encoder_outs21, src_resnet_outs12, src_resnet_outs21, T12, T21):
+    def swap(self, tsf_inputs, src_encoder_outs12, src_encoder_outs21, src_resnet_outs12, src_resnet_outs21, T12, T21, bg=None):
+        """networks/generator.py:245-275.  With ``bg`` (extension) also returns the composite m*bg + (1-m)*color of
+        models/swapper.py:268-269 from the head kernel."""
         ac = _align_corners()
         T12, T21 = T12.float().contiguous(), T21.float().contiguous()
         tsf = self.tsf_model._stream(tsf_inputs, True, 'swap')
@@ -792,7 +794,9 @@ class ImpersonatorGenerator(NetworkBase):
         tsf.encode(warp_srcs=enc, ac=ac)
         tsf.resnets(warp_srcs=res, ac=ac)
         tsf.decode()
-        tsf_img, tsf_mask, _ = tsf.heads()
+        tsf_img, tsf_mask, pred = tsf.heads(bg)
+        if bg is not None:
+            return tsf_img, tsf_mask, pred
         return tsf_img, tsf_mask
 
     @torch.no_grad()

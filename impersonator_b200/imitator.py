@@ -193,6 +193,19 @@ class Imitator(object):
     @_on_device
     @torch.no_grad()
     def personalize(self, src_path, src_smpl=None, output_path='', visualizer=None, src_img=None):
+        self.src_info = self._personalize(src_path, src_smpl, output_path, visualizer, src_img)
+        self.__dict__['_graphs'] = {}                    # captured chunk graphs hold the previous source's buffers
+
+    def _original_bg(self, bg_inputs, img_bg):
+        """--bg_model ORIGINAL: what the task keeps of the background net's output (models/imitator.py:130-131 keeps it
+        as it is; models/viewer.py:129 pastes it under the visible background)."""
+        return img_bg
+
+    def _extend_src_info(self, src_info):
+        """Task-specific additions to ``src_info`` (models/swapper.py:128-129 adds the part map)."""
+
+    def _personalize(self, src_path, src_smpl=None, output_path='', visualizer=None, src_img=None):
+        """The body shared by models/imitator.py:82-145, models/viewer.py:83-143 and models/swapper.py:99-165 -> src_info."""
         size = self._opt.image_size
         if src_img is None:
             img, ori_img = _read_image(src_path, size)
@@ -219,6 +232,7 @@ class Imitator(object):
         src_info['p2verts'] = p2verts.contiguous()
         if getattr(self._opt, 'only_vis', False):
             src_info['p2verts'] = self.render.get_vis_f2pts(src_info['p2verts'], tabs['fim']).contiguous()
+        self._extend_src_info(src_info)
         src_info['img'] = img
         src_info['image'] = ori_img
 
@@ -226,20 +240,19 @@ class Imitator(object):
         body_mask = 1 - bg_mask
         if self.bgnet is self.generator.bg_model:
             bg_inputs = torch.cat([img * bg_mask, bg_mask], dim=1)
-            src_info['bg'] = self.bgnet(bg_inputs)
+            src_info['bg'] = self._original_bg(bg_inputs, self.bgnet(bg_inputs))
         else:
             src_info['bg'] = self.bgnet(img, masks=body_mask, only_x=True)
         ft_mask = 1 - morph(src_info['cond'][:, -1:, :, :], ks=getattr(self._opt, 'ft_ks', 3), mode='erode')
         src_inputs = torch.cat([img * ft_mask, src_info['cond']], dim=1)
         src_info['src_inputs'] = src_inputs
         src_info['feats'] = self.generator.encode_src(src_inputs)
-        self.src_info = src_info
-        self.__dict__['_graphs'] = {}                    # captured chunk graphs hold the previous source's buffers
         if visualizer is not None:
             visualizer.vis_named_img('src', img)
             visualizer.vis_named_img('bg', src_info['bg'])
         if output_path and ori_img is not None:
             _save_image(ori_img, output_path, image_size=size)
+        return src_info
 
     # ---- per-frame geometry (models/imitator.py:216-268) --------------------------------------
     def swap_smpl(self, src_cam, src_shape, tgt_smpl, cam_strategy='smooth'):
@@ -296,7 +309,7 @@ class Imitator(object):
         tsf_info['fim'], tsf_info['wim'], tsf_info['cond'] = out['fim'], out['wim'], out['cond']
         tsf_info['tsf_img'], tsf_info['T'] = out['tsf_img'], out['T']
         self.tsf_info = tsf_info
-        preds = self.forward(out['tsf_inputs'], out['T'], host_layout=dict(hwc=hwc, u8=u8))
+        preds = self._forward_chunk(out['tsf_inputs'], out['T'], host_layout=dict(hwc=hwc, u8=u8))
         flag = self.generator.tsf_model.range_flag_tensor()            # operand-range bits of this chunk's pass
         flag = flag.clone() if flag is not None else None              # snapshot: the next pass zeroes the live flag
         return dict(tsf_info=tsf_info, preds=preds, hwc=self._out_hwc, u8=self._out_u8, flag=flag)
@@ -343,7 +356,13 @@ class Imitator(object):
     # ---- generator + composite (models/imitator.py:326-342) -----------------------------------
     @_on_device
     @torch.no_grad()
-    def forward(self, tsf_inputs, T, host_layout=None):
+    def forward(self, tsf_inputs, T):
+        """models/imitator.py:326-336 -> preds [B,3,H,W]."""
+        return self._forward_chunk(tsf_inputs, T)
+
+    @_on_device
+    @torch.no_grad()
+    def _forward_chunk(self, tsf_inputs, T, host_layout=None):
         """-> preds [B,3,H,W].  ``host_layout`` = dict(hwc=bool, u8=bool) additionally fills
         ``self._out_hwc`` / ``self._out_u8`` ([B,H,W,3] float32 / uint8 BGR, the output path of
         models/imitator.py:178-187) -- from the head kernel itself unless warp_front rewrites the frames."""
@@ -357,7 +376,7 @@ class Imitator(object):
         if front or not host_layout:
             color, mask, pred = self.generator.inference(enc, res, tsf_inputs, T, bg=self.src_info['bg'])
             if front:
-                pred = self.warp_front(pred, mask)
+                pred = Imitator.warp_front(self, pred, mask)     # subclasses (Viewer) redefine warp_front's signature
             if host_layout:
                 from . import kernels as K
                 hwc, u8 = K.frames_out(pred.contiguous(), want_hwc=hwc is not None, want_u8=u8 is not None)

@@ -124,6 +124,38 @@ def create_mapping(map_name, mapping_path='assets/pretrains/mapper.txt', part_in
     return map_fn
 
 
+def get_part_face_ids(part_type, mapping_path='assets/pretrains/mapper.txt', part_info=None, front_info=None, head_info=None,
+                      fill_back=False):
+    """utils/mesh.py:424-443 (+ :247-268, :327-365): the face ids of a part selection.  'par' -> ordered dict
+    part name -> face list (the parts must cover every face once); 'head_front' / 'head_back' -> face list."""
+    part_info = part_info or _sibling(mapping_path, 'smpl_part_info.json', 'assets/pretrains/smpl_part_info.json')
+    front_info = front_info or _sibling(mapping_path, 'front_face_1.json', 'assets/pretrains/front_face_1.json')
+    head_info = head_info or _sibling(mapping_path, 'head.json', 'assets/pretrains/head.json')
+    nf = get_f2vts(mapping_path, fill_back=fill_back).shape[0]
+    half = nf // 2
+
+    def both_sides(faces):
+        faces = list(faces)
+        return faces + [f + half for f in faces] if fill_back else faces
+
+    if part_type == 'par':
+        with open(part_info, 'r') as fp:
+            parts = json.load(fp)
+        ordered, seen = {}, set()
+        for name in sorted(parts.keys()):
+            ordered[name] = both_sides(parts[name]['face'])
+            seen |= set(ordered[name])
+        assert len(seen) == nf, 'nf_counter = {}, nf = {}'.format(len(seen), nf)
+        return ordered
+    if part_type == 'head_front':
+        return both_sides(_face_set(front_info))
+    if part_type == 'head_back':
+        return both_sides(set(_face_set(head_info)) - set(_face_set(front_info)))
+    if part_type == 'head':
+        raise NotImplementedError
+    raise ValueError('map name error {}'.format(part_type))
+
+
 def get_map_fn_dim(map_name):
     dims = {'seg': 1, 'uv': 2, 'uv_seg': 3, 'par': 11, 'ids': 1, 'binary': 15}
     if map_name not in dims:

@@ -144,6 +144,13 @@ class SMPLRenderer(nn.Module):
         return T.view(bs, self.image_size, self.image_size, 2)
 
     @staticmethod
+    def create_meshgrid(image_size):
+        """utils/nmr.py:491-504: the identity sampling grid [H,W,2] in [-1,1], (x, y) order."""
+        factor = (torch.arange(0, image_size, dtype=torch.float32) / (image_size - 1) - 0.5) * 2
+        xv, yv = torch.meshgrid([factor, factor], indexing='ij')
+        return torch.stack([yv, xv], dim=-1)
+
+    @staticmethod
     def get_vis_f2pts(f2pts, fims):
         """utils/nmr.py:506-546: keep visible faces' points, -2 elsewhere."""
         def get_vis(orig, fim):

@@ -266,13 +266,48 @@ def synthetic_hmr_state(template, seed=4):
     return sd
 
 
+class QuarterTurnBodyModel(object):
+    """A body model whose vertices are EXACT on every device: theta[3] = k selects a rotation of the UV-sphere body by
+    k quarter turns about y (a signed permutation of coordinates, no rounding), theta[0:3] = cam.  Used where a CPU-made
+    golden and the GPU path must rasterize bit-identical vertices (cos / sin differ by an ulp between devices)."""
+
+    def __init__(self, base_verts):
+        self.base = base_verts
+
+    def get_details(self, theta):
+        dev = theta.device
+        base = self.base.to(dev)
+        x, y, z = base[:, 0], base[:, 1], base[:, 2]
+        turned = [torch.stack(c, dim=1) for c in ((x, y, z), (z, y, -x), (-x, y, -z), (-z, y, x))]
+        ks = [int(round(float(k))) % 4 for k in theta[:, 3].tolist()]
+        verts = torch.stack([turned[k] for k in ks], dim=0).contiguous()
+        return {'theta': theta, 'cam': theta[:, 0:3].contiguous(), 'pose': theta[:, 3:75].contiguous(),
+                'shape': theta[:, 75:].contiguous(), 'verts': verts, 'j2d': None, 'j3d': None}
+
+
+def save_png(img, path):
+    """[3,H,W] float in [-1,1] -> 8-bit BGR png (what cv2.imread gives back to the loaders)."""
+    import cv2
+    a = ((img.permute(1, 2, 0).numpy() + 1) * 127.5).round().clip(0, 255).astype(np.uint8)
+    cv2.imwrite(path, a[..., ::-1].copy())
+
+
+def synthetic_part_info(n_parts=10):
+    """Stand-in for assets/pretrains/smpl_part_info.json (utils/mesh.py:247-268): ``n_parts`` named parts covering every
+    face once -- horizontal bands of the UV-sphere body (its faces are ordered ring by ring); part 0 is the top 30 %."""
+    head = int(0.3 * SMPL_F)                                      # part 0 (what PART_IDS['body'] leaves alone): a sizeable "head"
+    bounds = np.concatenate([[0], np.linspace(head, SMPL_F, n_parts).astype(int)])
+    return {"%02d_part" % i: {"face": list(range(int(bounds[i]), int(bounds[i + 1])))} for i in range(n_parts)}
+
+
 def write_synthetic_assets(root, image_size=256, n_targets=3, seed=0):
     """Everything ``Imitator(opt)`` loads from disk in the reference, as synthetic files with the real formats
     (README.md:48-68 lists the real downloads): under ``root``
 
       assets/pretrains/smpl_faces.npy       int faces [13776, 3]                       utils/nmr.py:137
       assets/pretrains/mapper.txt           obj-style v / vn / vt / f a/b/c records     utils/mesh.py:28-79
-      assets/pretrains/front_facial.json, head.json    {"face": [...]}                  utils/mesh.py:327-365
+      assets/pretrains/front_facial.json, front_face_1.json, head.json    {"face": [...]}   utils/mesh.py:214-245, 327-365
+      assets/pretrains/smpl_part_info.json  {part: {"face": [...]}} x 10                utils/mesh.py:247-268
       assets/pretrains/smpl_model.pkl       protocol-2 pickle (keys of batch_smpl.py:236-283)
       assets/pretrains/hmr_tf2pt.pth        HumanModelRecovery.state_dict()             models/imitator.py:69-74
       outputs/checkpoints/G.pth             ImpersonatorGenerator.state_dict()          models/imitator.py:58-59
@@ -307,6 +342,8 @@ def write_synthetic_assets(root, image_size=256, n_targets=3, seed=0):
     front = sorted(rs.choice(head, size=500, replace=False).tolist())
     json.dump({"face": front}, open(os.path.join(pre, "front_facial.json"), "w"))
     json.dump({"face": head}, open(os.path.join(pre, "head.json"), "w"))
+    json.dump({"face": front}, open(os.path.join(pre, "front_face_1.json"), "w"))
+    json.dump(synthetic_part_info(), open(os.path.join(pre, "smpl_part_info.json"), "w"))
     smpl = synthetic_smpl_model(seed=3)
     with open(os.path.join(pre, "smpl_model.pkl"), "wb") as fp:
         pickle.dump(smpl, fp, protocol=2)

@@ -1,0 +1,79 @@
+"""oracle/tasks_ref.py (Viewer.view / Swapper.swap restated on CPU) against tests/golden/tasks.npz, the slices the
+reference's own models/viewer.py and models/swapper.py produced on the same synthetic inputs."""
+import numpy as np
+import torch
+
+import tasks_common as C
+from impersonator_b200 import synthetic as S
+from impersonator_b200.generator import ImpersonatorGenerator
+from oracle import tasks_ref as T
+
+
+def _setup(tmp_path):
+    torch.set_grad_enabled(False)
+    g = np.load(C.GOLD)
+    v, f = S.uv_sphere()
+    tabs = S.synthetic_tables()
+    sd = S.fill_state_dict(ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6).state_dict(), seed=0)
+    a_png, b_png = C.write_inputs(tmp_path)
+    body = S.QuarterTurnBodyModel(v)
+    return g, v, f, tabs, sd, a_png, b_png, body
+
+
+def test_oracle_view_matches_reference_viewer(tmp_path):
+    g, v, f, tabs, sd, a_png, _, body = _setup(tmp_path)
+    d = body.get_details(torch.from_numpy(g["src_theta"])[None])
+    info = T.personalize(C.read_like_reference(a_png), d["cam"], d["verts"], f, tabs, sd, C.SIZE, "viewer")
+    assert np.abs(C.sl(info["bg"]) - g["view_src_bg"]).max() < 1e-5
+    assert np.array_equal(C.sl(info["cond"]), g["view_src_cond"])
+    for tag, kw in (("plain", {}), ("front_bg", dict(front_warp=True, bg_replace=True))):
+        for i, (rt, t) in enumerate(g["views"]):
+            preds, _ = T.view(info, rt / 180 * np.pi, t, f, tabs, sd, C.SIZE, **kw)
+            err = np.abs(C.sl(preds) - g["view_%s_%d" % (tag, i)]).max()
+            print("view %s %d: oracle vs reference max-abs %.2e" % (tag, i, err))
+            assert err < 1e-5
+
+
+def test_oracle_swap_matches_reference_swapper(tmp_path):
+    g, v, f, tabs, sd, a_png, b_png, body = _setup(tmp_path)
+    _, part_fn, part_faces = C.part_table(f.shape[0])
+    infos = []
+    for png, key in ((a_png, "src_theta"), (b_png, "tgt_theta")):
+        d = body.get_details(torch.from_numpy(g[key])[None])
+        infos.append(T.personalize(C.read_like_reference(png), d["cam"], d["verts"], f, tabs, sd, C.SIZE, "swapper", part_fn))
+    src, tgt = infos
+    assert np.array_equal(src["part"][:, :, 1::4, 2::4].numpy(), g["swap_src_part"])
+    assert np.abs(C.sl(tgt["bg"]) - g["swap_tgt_bg"]).max() < 1e-5
+    for tag, fw in (("plain", False), ("front", True)):
+        for part in ("body", "all"):
+            preds, T11, T21 = T.swap(src, tgt, part_faces, tabs, sd, C.SIZE, part, front_warp=fw)
+            err = np.abs(C.sl(preds) - g["swap_%s_%s" % (tag, part)]).max()
+            print("swap %s %s: oracle vs reference max-abs %.2e" % (tag, part, err))
+            assert err < 1e-5
+            if tag == "plain" and part == "body":
+                assert np.array_equal(T11[:, 1::4, 2::4].numpy(), g["swap_T11"])
+                assert np.abs(T21[:, 1::4, 2::4].numpy() - g["swap_T21"]).max() < 1e-6
+
+
+def test_product_host_helpers_match_oracle():
+    """Device-agnostic host logic of the mirrors (no kernels involved): Euler matrix, rigid transform, camera swap."""
+    from impersonator_b200.swapper import Swapper
+    from impersonator_b200.viewer import Viewer, euler2matrix
+    rs = np.random.RandomState(3)
+    for _ in range(5):
+        rt = (rs.rand(3) * 2 - 1) * np.pi
+        assert np.array_equal(euler2matrix(rt.astype(np.float32)), T.euler2matrix(rt.astype(np.float32)))
+    X = torch.from_numpy(rs.randn(1, 50, 3).astype(np.float32))
+    rt, t = np.array([0.2, -1.1, 0.4], np.float32), np.array([0.1, 0.0, -0.3], np.float32)
+    got = Viewer.rotate_trans(None, rt, t, X)
+    want = torch.bmm(X, torch.from_numpy(T.euler2matrix(rt))[None]) + torch.from_numpy(t)[None, None]
+    assert (got - want).abs().max().item() < 1e-6
+    many = Viewer.rotate_trans(None, np.stack([rt, rt * 2]), t, X)
+    assert many.shape == (2, 50, 3) and torch.equal(many[0:1], got)
+    src_cam = torch.tensor([[0.9, 0.1, -0.2]])
+    tgt = torch.zeros(1, 85)
+    tgt[0, 0:3] = torch.tensor([1.2, 0.05, 0.02])
+    keep = tgt.clone()
+    out = Swapper.swap_smpl(None, src_cam, torch.zeros(1, 10), tgt)
+    assert torch.equal(tgt, keep)                                       # the caller's vector is not edited
+    assert torch.allclose(out[0, 0:3], torch.tensor([0.9, 0.15, -0.18]))   # models/swapper.py:183-186: scale of A, shifts add up
