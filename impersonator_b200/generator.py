@@ -38,6 +38,12 @@ DEFAULT_PRECISION = "fp16f8"
 
 
 _WEIGHTS_EPOCH = [0]
+_PASS = [0]                                              # bumped by every ImpersonatorGenerator entry point; streams stamp it
+
+
+def _new_pass():
+    _PASS[0] += 1
+
 
 
 def weights_epoch():
@@ -180,15 +186,18 @@ class NetworkBase(nn.Module):
                 m.__dict__['_lwb_precision'] = mode
 
     def range_flags(self):
-        """-> list of int32[1] device tensors, one per live stream: bit 0 = an activation left the e4m3 correction
+        """-> list of int32[1] device tensors, one per stream used by the most recent pass: bit 0 = an activation left the e4m3 correction
         range (|x| >= 1024, fp16f8 precision degrades for those elements), bit 1 = the fp16 range (|x| >= 60000 / NaN),
         bit 2 = output-head pre-activations of +-8 and more in fp16f8 mode (its ~1e-4 relative end-to-end precision then
         no longer guarantees 1e-3 on the pixels: use fp16x3)."""
-        flags = []
+        live = []
         for m in self.modules():
             for st in getattr(m, '_lwb_streams', {}).values():
-                flags.append(st.range_flag)
-        return flags
+                live.append((getattr(st, 'pass_id', -1), st.range_flag))
+        if not live:
+            return []
+        last = max(p for p, _ in live)                       # streams of other shapes / precisions keep the bits of older passes
+        return [f for p, f in live if p == last]
 
     def range_flag_tensor(self):
         """One int32 device scalar = OR over the live streams' flags; None if no stream exists yet.  No host sync."""
@@ -351,6 +360,7 @@ class _StreamBase(object):
     def begin_pass(self):
         """Zero the InstanceNorm statistics and the range flag (one fill)."""
         self._zero.zero_()
+        self.pass_id = _PASS[0]
 
     def _conv_norm(self, L, out, relu, residual=None, warp_src=None, T=None, ac=False):
         if L.fusable:
@@ -761,11 +771,13 @@ class ImpersonatorGenerator(NetworkBase):
         return img_bg, src_img, src_mask, tsf_img, tsf_mask
 
     def encode_src(self, src_inputs):
+        _new_pass()
         return self.src_model.inference(src_inputs)
 
     @torch.no_grad()
     def infer_front(self, src_inputs, tsf_inputs, T):
         ac = _align_corners()
+        _new_pass()
         T = T.float().contiguous()
         src = self.src_model._stream(src_inputs, True, 'front')
         src.load_input(src_inputs.float())
@@ -786,6 +798,7 @@ class ImpersonatorGenerator(NetworkBase):
         """networks/generator.py:245-275.  With ``bg`` (extension) also returns the composite m*bg + (1-m)*color of
         models/swapper.py:268-269 from the head kernel."""
         ac = _align_corners()
+        _new_pass()
         T12, T21 = T12.float().contiguous(), T21.float().contiguous()
         tsf = self.tsf_model._stream(tsf_inputs, True, 'swap')
         tsf.load_input(tsf_inputs.float())
@@ -806,6 +819,7 @@ class ImpersonatorGenerator(NetworkBase):
         (caller-allocated [B,H,W,3] float32 / uint8-BGR) receive the same frames in the layouts of the output
         path (models/imitator.py:178-180, utils/cv_utils.py:23-36) from that launch."""
         ac = _align_corners()
+        _new_pass()
         if (pred_hwc is not None or pred_u8 is not None) and bg is None:
             raise LwbError("pred_hwc / pred_u8 need bg (they hold the composite)")
         tsf_inputs = tsf_inputs.float().contiguous()

@@ -35,6 +35,14 @@ def test_generator_streams_match_oracle(monkeypatch):
     refs = G.forward(inp["bg"], inp["src"], inp["tsf"][:1], inp["T"][:1], sd)
     assert max((a - b).abs().max().item() for a, b in zip(outs, refs)) < 2e-4
     assert n.range_status() == 0
+    # range bits are reported for the streams of the most recent pass only: a stale bit of another shape does not leak
+    n.inference(enc, res, inp["tsf"], inp["T"])
+    stale = next(st for k, st in n.tsf_model._lwb_streams.items() if k[1] == 2)
+    n.inference(enc, res, inp["tsf"][:1], inp["T"][:1])
+    stale.range_flag.fill_(4)
+    assert len(n.tsf_model.range_flags()) == 1 and n.tsf_model.range_status() == 0
+    n.inference(enc, res, inp["tsf"], inp["T"])
+    assert n.tsf_model.range_status() == 0                         # the pass zeroes its own flag first
 
 
 def test_hmr_stream_matches_oracle(monkeypatch):
