@@ -343,6 +343,27 @@ def main():
         cam, verts = dev_sets[i % len(dev_sets)]
         return step_body(cam, verts)
 
+    # Operand-precision policy, as Imitator.inference applies it: if the default fp16f8 mode raises a range bit on this
+    # rank's frames (bit 0: |x| >= 1024, bit 2: head pre-activations beyond +-8), the rank runs fp16x3 -- `value` is
+    # measured under the product's own policy on every rank, never in a mode the API would have left.
+    policy_bits = 0
+    for i in range(len(dev_sets)):
+        step_eager(i)
+        policy_bits |= net.tsf_model.range_status()
+    if policy_bits & 2:
+        raise SystemExit("bench: activations beyond the fp16 range on rank %d" % rank)
+    if (policy_bits & 5) and mode == "fp16f8" and os.environ.get("LWB_AUTO_PRECISION", "1") != "0":
+        net.set_precision("fp16x3")
+        imitator.personalize("", src_smpl=src_theta.numpy(), src_img=src_img)
+        enc, res = imitator.src_info["feats"]
+        bg = imitator.src_info["bg"]
+        p2v, simg = imitator.src_info["p2verts"], imitator.src_info["img"]
+        mode = "fp16x3"
+    modes_by_rank = [mode]
+    if world > 1:
+        modes_by_rank = [None] * world
+        dist.all_gather_object(modes_by_rank, mode)
+
     # LWB_GRAPH (default on): the step's launch sequence is captured once and replayed (one cudaGraphLaunch per step); the
     # frame set of the step is copied device-to-device into the graph's static input (1.3 MB), still "resident in HBM"
     from impersonator_b200.graph import CapturedStep, graphs_enabled
@@ -487,11 +508,14 @@ def main():
         hmr_leg = {"ms_per_frame": h0.elapsed_time(h1) / 10 / B, "batch": B,
                    "what": "HumanModelRecovery.forward (pre-activation ResNet-50 @224^2 on the conv engine + 3-iteration regressor); "
                            "added per frame when Imitator.inference is driven from images (tgt_smpls=None)"}
-    run_e2e(max(args.steps, 3), 0)                  # warm-up call of the same length (also warms the pinned-host allocator)
-    ms_e2e = timed_call(lambda: run_e2e(args.steps, 1))
+    # warm-up call = the same sequence (same first frame, hence the same 'smooth' cameras as the device-resident sets): the
+    # pinned-host allocator is warm, the chunk graph captured, and a range-bit switch to fp16x3 -- a one-time event per
+    # source and sequence -- has happened before the timed call, which then measures the steady state of the API
+    run_e2e(max(args.steps, 3), 0)
+    ms_e2e = timed_call(lambda: run_e2e(args.steps, 0))
     e2e_fps = world * B * args.steps / (ms_e2e * 1e-3)
     run_e2e(max(args.steps, 3), 0, as_uint8=True)
-    ms_u8 = timed_call(lambda: run_e2e(args.steps, 1, as_uint8=True))
+    ms_u8 = timed_call(lambda: run_e2e(args.steps, 0, as_uint8=True))
     h2d = B * 85 * 4
     d2h = B * 3 * size * size * 4
 
@@ -509,6 +533,9 @@ def main():
                     "uint8_frames": {"value": world * B * args.steps / (ms_u8 * 1e-3), "unit": "frames/s",
                                      "d2h_bytes_per_step": B * 3 * size * size,
                                      "note": "same call with as_uint8=True: the BGR uint8 images the reference writes to disk"}},
+            "precision": {"by_rank": modes_by_rank, "range_bits_rank0": policy_bits,
+                          "policy": "default fp16f8; a rank whose frames raise a range bit (|x| >= 1024 or head pre-activations "
+                                    "beyond +-8) runs fp16x3, exactly as Imitator.inference switches (LWB_AUTO_PRECISION)"},
             "gpu_launches": launches, "clocks": clocks, "steady_state": steady, "parity": parity, "config3_stream64": c3,
             "init_broadcast": {"bytes": bc_stats.get("bytes"), "ms": bc_stats.get("ms"),
                                "what": "the ONE collective: generator weights + source image, rank 0 -> all (NCCL), outside the timed region"},
@@ -580,6 +607,8 @@ def main():
         line["breakdown_ms_per_step"] = {k: prof[k]["ms"] / prof["passes"] for k in ("conv", "norm", "heads", "correspond", "input")}
         # the other precision modes of the conv engine, for transparency (the headline is the default mode)
         had = os.environ.get("LWB_PRECISION")
+        pinned_mode = getattr(net, '_lwb_precision', None)
+        net.set_precision(None)                                  # follow LWB_PRECISION for these legs (a policy switch pins the mode)
         try:
             modes, ref_pred = {}, None
             for m in ("fp16x3", "fp16f8", "fp16"):
@@ -597,6 +626,7 @@ def main():
             line["precision_modes"] = modes
             line["fast_mode"] = dict(modes["fp16"], precision="single-pass fp16")
         finally:
+            net.set_precision(pinned_mode)
             if had is None:
                 os.environ.pop("LWB_PRECISION", None)
             else:
