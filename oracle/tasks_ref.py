@@ -93,3 +93,29 @@ def swap(src_info, tgt_info, part_faces, tabs, sd, size, target_part='body', fro
         front = nmr_ref.encode_fim(src_info['fim'], tabs["front_map_fn"])
         preds = (1 - front) * preds + src_info['img'] * front * (1 - mask)
     return preds, T11, T21
+
+
+def imitate(src_info, src_shape, thetas, body, faces, tabs, sd, size, cam_strategy='smooth', front_warp=False):
+    """Imitator.inference_by_smpls (models/imitator.py:192-268, 326-342): per frame swap_smpl -> body model -> raster +
+    correspondence -> generator.inference + composite (+ warp_front).  thetas [N,85] -> list of HxWx3 arrays, last T."""
+    outs, first_cam, T = [], None, None
+    for t in range(thetas.shape[0]):
+        th = thetas[t:t + 1]
+        if t == 0 and cam_strategy == 'smooth':
+            first_cam = th[:, 0:3].clone()
+        if cam_strategy == 'smooth':
+            cam = src_info['cam'].clone()
+            cam[:, 1:] += th[:, 1:3] - first_cam[:, 1:]
+        elif cam_strategy == 'source':
+            cam = src_info['cam']
+        else:
+            cam = th[:, 0:3]
+        d = body.get_details(torch.cat([cam, th[:, 3:75], src_shape], dim=1))
+        c = nmr_ref.correspond(d['cam'], d['verts'], faces, tabs["map_fn"], src_info['p2verts'], src_info['img'], size)
+        preds, _, mask = G.imitator_forward(src_info['bg'], src_info['feats'], c['tsf_inputs'], c['T'], sd)
+        if front_warp:
+            front = nmr_ref.encode_fim(c['fim'], tabs["front_map_fn"])
+            preds = (1 - front) * preds + c['tsf_img'] * front * (1 - mask)
+        outs.append(preds[0].permute(1, 2, 0).numpy())
+        T = c['T']
+    return outs, T

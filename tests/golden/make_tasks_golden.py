@@ -1,8 +1,11 @@
 """Generates tests/golden/tasks.npz -- run ONLY in the build container (needs /root/reference).
 
-Pins the two task classes next to the Imitator -- novel-view synthesis and appearance transfer -- to the reference's OWN
-code: ``models/viewer.py`` and ``models/swapper.py`` are imported unmodified from /root/reference and their methods run
-as unbound functions, on CPU, on a namespace that carries the attributes they read:
+Pins the three task classes -- motion imitation, novel-view synthesis and appearance transfer -- to the reference's OWN
+code: ``models/imitator.py``, ``models/viewer.py`` and ``models/swapper.py`` are imported unmodified from /root/reference
+and their methods run as unbound functions, on CPU, on a namespace that carries the attributes they read:
+
+  Imitator.personalize / inference_by_smpls / transfer_params_by_smpl / swap_smpl / forward / warp_front
+                       models/imitator.py:82-145, 192-268, 326-342 (cam strategies smooth / source / target, front_warp)
 
   Viewer.personalize   models/viewer.py:83-143      Swapper.personalize     models/swapper.py:99-165
   Viewer.rotate_trans  :237-244                     Swapper.swap            :199-239
@@ -44,6 +47,11 @@ SRC_THETA[0:3] = (0.95, 0.03, -0.02)
 TGT_THETA = np.zeros(85, np.float32)
 TGT_THETA[0:3] = (1.05, -0.04, 0.05)
 TGT_THETA[3] = 1.0                                            # a quarter turn: person B is seen from the side
+IMIT_THETAS = np.zeros((3, 85), np.float32)                   # driving frames of the Imitator: quarter turns 0, 1, 3
+IMIT_THETAS[:, 0] = (0.9, 1.0, 1.08)
+IMIT_THETAS[:, 1] = (0.02, -0.05, 0.06)
+IMIT_THETAS[:, 2] = (0.01, 0.04, -0.03)
+IMIT_THETAS[:, 3] = (0.0, 1.0, 3.0)
 VIEWS = [((10.0, 45.0, 10.0), (0.0, 0.0, 0.0)), ((0.0, 200.0, -5.0), (0.05, -0.02, 0.0))]       # degrees, translation
 
 
@@ -102,6 +110,22 @@ def main():
     with tempfile.TemporaryDirectory() as tmp, torch12_grid_sample():
         a_png, b_png = write_inputs(tmp)
 
+        # ---- motion imitation: the reference Imitator itself (models/imitator.py:82-145, 192-268, 326-342) ----
+        from models.imitator import Imitator
+        for tag, opt, strategy in (("smooth", {}, "smooth"), ("front_source", dict(front_warp=True), "source"),
+                                   ("target", {}, "target")):
+            im = task(Imitator, **opt)
+            im.src_info = im.tsf_info = im.first_cam = None
+            im.personalize(a_png, src_smpl=SRC_THETA.copy())
+            frames = im.inference_by_smpls([th.copy() for th in IMIT_THETAS], cam_strategy=strategy)
+            assert len(frames) == 3 and frames[0].shape == (SIZE, SIZE, 3)
+            for t, fr in enumerate(frames):
+                out["imit_%s_%d" % (tag, t)] = fr[1::4, 2::4].copy()
+            if tag == "smooth":
+                out["imit_src_bg"] = sl(im.src_info["bg"])
+                out["imit_last_T"] = im.tsf_info["T"][:, 1::4, 2::4].numpy()
+                out["imit_last_cam"] = im.tsf_info["cam"].numpy()
+
         # ---- novel views ---------------------------------------------------------------------
         for tag, opt in (("plain", {}), ("front_bg", dict(front_warp=True, bg_replace=True))):
             vw = task(Viewer, **opt)
@@ -142,7 +166,7 @@ def main():
                 out["swap_src_part"] = sw.src_info["part"][:, :, 1::4, 2::4].numpy()
                 out["swap_tgt_bg"] = sl(sw.tsf_info["bg"])
     out["views"] = np.array(VIEWS, dtype=np.float32)
-    out["src_theta"], out["tgt_theta"] = SRC_THETA, TGT_THETA
+    out["src_theta"], out["tgt_theta"], out["imit_thetas"] = SRC_THETA, TGT_THETA, IMIT_THETAS
     np.savez_compressed(os.path.join(HERE, "tasks.npz"), **out)
     print("wrote tasks.npz", {k: v.shape for k, v in out.items()})
 

@@ -77,3 +77,20 @@ def test_product_host_helpers_match_oracle():
     out = Swapper.swap_smpl(None, src_cam, torch.zeros(1, 10), tgt)
     assert torch.equal(tgt, keep)                                       # the caller's vector is not edited
     assert torch.allclose(out[0, 0:3], torch.tensor([0.9, 0.15, -0.18]))   # models/swapper.py:183-186: scale of A, shifts add up
+
+
+def test_oracle_imitation_matches_reference_imitator(tmp_path):
+    """The oracle's per-frame loop against what the reference's own Imitator.personalize + inference_by_smpls returned
+    (camera strategies smooth / source / target, with and without front_warp)."""
+    g, v, f, tabs, sd, a_png, _, body = _setup(tmp_path)
+    d = body.get_details(torch.from_numpy(g["src_theta"])[None])
+    info = T.personalize(C.read_like_reference(a_png), d["cam"], d["verts"], f, tabs, sd, C.SIZE, "imitator")
+    assert np.abs(C.sl(info["bg"]) - g["imit_src_bg"]).max() < 1e-5
+    thetas = torch.from_numpy(g["imit_thetas"])
+    for tag, strategy, fw in (("smooth", "smooth", False), ("front_source", "source", True), ("target", "target", False)):
+        outs, lastT = T.imitate(info, d["shape"], thetas, body, f, tabs, sd, C.SIZE, strategy, front_warp=fw)
+        for t, fr in enumerate(outs):
+            err = np.abs(fr[1::4, 2::4] - g["imit_%s_%d" % (tag, t)]).max()
+            assert err < 1e-5, (tag, t, err)
+        if tag == "smooth":
+            assert np.abs(lastT[:, 1::4, 2::4].numpy() - g["imit_last_T"]).max() < 1e-6

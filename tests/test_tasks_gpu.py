@@ -137,3 +137,26 @@ def test_run_view_and_run_swap_from_asset_files(cuda, tmp_path, monkeypatch):
     assert preds.shape == (1, 3, 256, 256) and torch.isfinite(preds).all() and preds.abs().max().item() <= 1.5
     other = swapper.swap(src_info=swapper.src_info, tgt_info=swapper.tsf_info, target_part='all')
     assert (other - preds).abs().max().item() > 1e-3                   # part 0 comes from person A in 'body' mode only
+
+
+@pytest.mark.parametrize("tag,strategy,front,batch", [("smooth", "smooth", False, 4), ("front_source", "source", True, 2),
+                                                      ("target", "target", False, 1)])
+def test_imitator_matches_reference_imitator(cuda, world, tag, strategy, front, batch):
+    """``Imitator.personalize`` + ``inference_by_smpls`` against the frames the reference's own ``models/imitator.py`` returned
+    for the same source image file, SMPL vectors and weights (tests/golden/tasks.npz): three camera strategies, with and
+    without front_warp, chunk sizes 4 / 2 / 1 (the reference runs frame by frame)."""
+    from impersonator_b200.imitator import Imitator
+    w, g = world, world["g"]
+    opt = C.Opt()
+    opt.front_warp, opt.batch_size = front, batch
+    im = Imitator(opt, generator=w["net"], hmr=S.QuarterTurnBodyModel(w["v"]), render=_render(w, front), device=cuda)
+    im.personalize(w["a"], src_smpl=g["src_theta"].copy())
+    assert np.abs(C.sl(im.src_info["bg"]) - g["imit_src_bg"]).max() < TOL
+    frames = im.inference_by_smpls([th.copy() for th in g["imit_thetas"]], cam_strategy=strategy)
+    assert len(frames) == 3
+    errs = [float(np.abs(fr[1::4, 2::4] - g["imit_%s_%d" % (tag, t)]).max()) for t, fr in enumerate(frames)]
+    print("Imitator %s (chunks of %d) vs the reference Imitator: %s" % (tag, batch, ["%.2e" % e for e in errs]))
+    assert max(errs) < TOL
+    if tag == "smooth":
+        assert np.abs(im.tsf_info["T"][:, 1::4, 2::4].cpu().numpy() - g["imit_last_T"]).max() < 1e-5
+        assert np.abs(im.tsf_info["cam"].cpu().numpy() - g["imit_last_cam"]).max() < 1e-6
