@@ -40,6 +40,22 @@ def test_renderer_tables_from_asset_files(tmp_path, monkeypatch):
                 mine = mesh.create_mapping(name, "assets/pretrains/mapper.txt", contain_bg=True, fill_back=fb)
                 ref = R.create_mapping(name, "assets/pretrains/mapper.txt", contain_bg=True, fill_back=fb)
                 assert mine.dtype == ref.dtype and np.array_equal(mine, ref), (name, fb)
+        for fb in (False, True):                                  # the Swapper's tables (models/swapper.py:34-37)
+            if fb:                                                # upstream's 'par' table does not support fill_back either
+                for fn in (mesh.create_mapping, R.create_mapping):
+                    with pytest.raises(AssertionError):
+                        fn('par', "assets/pretrains/mapper.txt", contain_bg=True, fill_back=True)
+            else:
+                mine = mesh.create_mapping('par', "assets/pretrains/mapper.txt", contain_bg=True, fill_back=False)
+                ref = R.create_mapping('par', "assets/pretrains/mapper.txt", contain_bg=True, fill_back=False)
+                assert mine.shape == ref.shape == (13776 + 1, 11) and np.array_equal(mine, ref)
+            mine_ids = mesh.get_part_face_ids('par', "assets/pretrains/mapper.txt", fill_back=fb)
+            ref_ids = R.get_part_face_ids('par', "assets/pretrains/mapper.txt", fill_back=fb)
+            assert list(mine_ids.keys()) == list(ref_ids.keys())
+            assert all(list(mine_ids[k]) == list(ref_ids[k]) for k in ref_ids), fb
+            for kind in ('head_front', 'head_back'):
+                assert sorted(mesh.get_part_face_ids(kind, "assets/pretrains/mapper.txt", fill_back=fb)) == \
+                    sorted(R.get_part_face_ids(kind, "assets/pretrains/mapper.txt", fill_back=fb)), (kind, fb)
 
 
 def test_networks_factory_names():
