@@ -286,6 +286,46 @@ def heads_composite(raw, bg=None, want_color=True, want_mask=True, color=None, m
     return tuple(outs)
 
 
+def correspond(cam, verts, face_idx, image_size, map_fn, src_p2verts, src_img=None, align_corners=None,
+               want_f2verts=False, near=None, far=None, out=None):
+    """lwb_correspond's contract through the CPU oracle (oracle/nmr_ref.py + the C rasterizer restatement)."""
+    from oracle import nmr_ref
+    ac = K.default_align_corners() if align_corners is None else align_corners
+    img = src_img if src_img is not None else torch.zeros(1, 3, image_size, image_size)
+    c = nmr_ref.correspond(cam, verts, face_idx, map_fn, src_p2verts, img, image_size, align_corners=ac)
+    res = dict(fim=c["fim"], wim=c["wim"], T=c["T"], tsf_inputs=c["tsf_inputs"].contiguous(),
+               f2verts=c["f2verts"] if want_f2verts else None)
+    res["tsf_img"] = res["tsf_inputs"][:, :3]
+    res["cond"] = res["tsf_inputs"][:, 3:]
+    return res
+
+
+def warp_nchw(x, T, align_corners=None, out=None, accumulate=False):
+    ac = K.default_align_corners() if align_corners is None else align_corners
+    y = torch.nn.functional.grid_sample(x.expand(T.shape[0], -1, -1, -1), T, mode='bilinear', padding_mode='zeros',
+                                        align_corners=ac)
+    if out is not None:
+        out.copy_(out + y if accumulate else y)
+        return out
+    return y
+
+
+def install_tasks(monkeypatch):
+    """install() + the correspondence / warp front-ends and the renderer's CUDA-only guard: enough to run the task classes'
+    personalize / view / swap on CPU (Imitator.inference itself drives CUDA streams and stays GPU-only)."""
+    from impersonator_b200 import nmr
+    install(monkeypatch)
+    monkeypatch.setattr(K, "correspond", correspond)
+    monkeypatch.setattr(K, "warp_nchw", warp_nchw)
+
+    def _correspond(self, cam, vertices, src_p2verts, src_img, want_f2verts=False, align_corners=None):
+        if src_p2verts is None:
+            src_p2verts = torch.zeros((1, self.nf, 3, 2), dtype=torch.float32)
+        return correspond(cam.float(), vertices.float(), self.faces, self.image_size, self.map_fn, src_p2verts.float(),
+                          src_img, align_corners=align_corners, want_f2verts=want_f2verts)
+    monkeypatch.setattr(nmr.SMPLRenderer, "_correspond", _correspond)
+
+
 def install(monkeypatch):
     for name in ("pack_conv_weight", "pack_conv_weight_rowk", "ConvPlan", "norm_act_nhwc", "nchw_to_nhwc_split", "nhwc_to_nchw",
                  "conv2d_direct_nchw", "gated_bn_nchw", "gated_act_nhwc", "self_attention_nhwc", "maxpool_nchw_to_nhwc",

@@ -94,3 +94,79 @@ def test_oracle_imitation_matches_reference_imitator(tmp_path):
             assert err < 1e-5, (tag, t, err)
         if tag == "smooth":
             assert np.abs(lastT[:, 1::4, 2::4].numpy() - g["imit_last_T"]).max() < 1e-6
+
+
+def test_viewer_and_swapper_host_logic_on_cpu(tmp_path, monkeypatch):
+    """The product's Viewer / Swapper classes themselves, on CPU: every kernel front-end replaced by its torch stand-in
+    (tests/kernel_emulator.py, contracts of include/lwb_b200.h), compared with what the reference's models/viewer.py and
+    models/swapper.py produced (tests/golden/tasks.npz).  Covers the orchestration the GPU tests cover, without a GPU:
+    personalize (masks, background paste, part map), rotate_trans, bg_replace / front_warp, T11 / T21, the two-source swap."""
+    import kernel_emulator
+    from impersonator_b200.nmr import SMPLRenderer
+    from impersonator_b200.swapper import Swapper
+    from impersonator_b200.viewer import Viewer
+    kernel_emulator.install_tasks(monkeypatch)
+    g, v, f, tabs, sd, a_png, b_png, body = _setup(tmp_path)
+    net = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6).eval()
+    net.load_state_dict(sd)
+
+    def render(front):
+        return SMPLRenderer(image_size=C.SIZE, faces=f.numpy(), map_fn=tabs["map_fn"], has_front=front,
+                            front_map_fn=tabs["front_map_fn"], back_map_fn=tabs["back_map_fn"])
+    worst = 0.0
+    for tag, front, bg_replace in (("plain", False, False), ("front_bg", True, True)):
+        opt = C.Opt()
+        opt.front_warp, opt.bg_replace = front, bg_replace
+        vw = Viewer(opt, generator=net, hmr=body, render=render(front), device="cpu")
+        vw.personalize(a_png, src_smpl=g["src_theta"].copy())
+        assert np.array_equal(C.sl(vw.src_info["cond"]), g["view_src_cond"])
+        for i, (rt, t) in enumerate(g["views"]):
+            preds = vw.view(rt / 180 * np.pi, t, name=str(i))
+            worst = max(worst, float(np.abs(C.sl(preds) - g["view_%s_%d" % (tag, i)]).max()))
+    part_info, _, part_faces = C.part_table(f.shape[0])
+    for tag, front in (("plain", False), ("front", True)):
+        opt = C.Opt()
+        opt.front_warp = front
+        sw = Swapper(opt, part_info=part_info, generator=net, hmr=body, render=render(front), device="cpu")
+        sw.swap_setup(a_png, b_png, src_smpl=g["src_theta"].copy(), tgt_smpl=g["tgt_theta"].copy())
+        assert np.array_equal(sw.src_info["part"][:, :, 1::4, 2::4].numpy(), g["swap_src_part"])
+        for part in ("body", "all"):
+            preds = sw.swap(sw.src_info, sw.tsf_info, target_part=part)
+            worst = max(worst, float(np.abs(C.sl(preds) - g["swap_%s_%s" % (tag, part)]).max()))
+        if tag == "plain":
+            mask = torch.sum(sw.src_info["part"][:, [0], ...], dim=1).bool()
+            T11, T21 = sw.calculate_trans(mask, sorted(set(part_faces[0])))
+            assert np.array_equal(T11[:, 1::4, 2::4].numpy(), g["swap_T11"])
+            assert np.abs(T21[:, 1::4, 2::4].numpy() - g["swap_T21"]).max() < 1e-6
+    print("Viewer / Swapper on the kernel emulator vs the reference's frames: max-abs %.2e" % worst)
+    assert worst < 2e-4
+
+
+def test_imitator_per_frame_api_host_logic_on_cpu(tmp_path, monkeypatch):
+    """The Imitator mirror's per-frame methods as the reference's loop calls them (models/imitator.py:198-203:
+    transfer_params_by_smpl + forward), on the kernel emulator, against the reference Imitator's frames.  (The chunked
+    ``inference`` drives CUDA streams / pinned memory and is covered by the GPU tests.)"""
+    import kernel_emulator
+    from impersonator_b200.imitator import Imitator
+    from impersonator_b200.nmr import SMPLRenderer
+    kernel_emulator.install_tasks(monkeypatch)
+    g, v, f, tabs, sd, a_png, _, body = _setup(tmp_path)
+    net = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6).eval()
+    net.load_state_dict(sd)
+    worst = 0.0
+    for tag, strategy, front in (("smooth", "smooth", False), ("front_source", "source", True), ("target", "target", False)):
+        opt = C.Opt()
+        opt.front_warp = front
+        render = SMPLRenderer(image_size=C.SIZE, faces=f.numpy(), map_fn=tabs["map_fn"], has_front=front,
+                              front_map_fn=tabs["front_map_fn"], back_map_fn=tabs["back_map_fn"])
+        im = Imitator(opt, generator=net, hmr=body, render=render, device="cpu")
+        im.personalize(a_png, src_smpl=g["src_theta"].copy())
+        for t, th in enumerate(g["imit_thetas"]):
+            tsf_inputs = im.transfer_params_by_smpl(th.copy(), strategy, t=t)
+            preds = im.forward(tsf_inputs, im.tsf_info['T'])
+            fr = preds[0].permute(1, 2, 0).numpy()
+            worst = max(worst, float(np.abs(fr[1::4, 2::4] - g["imit_%s_%d" % (tag, t)]).max()))
+        if tag == "smooth":
+            assert np.abs(im.tsf_info["T"][:, 1::4, 2::4].numpy() - g["imit_last_T"]).max() < 1e-6
+    print("Imitator per-frame API on the kernel emulator vs the reference's frames: max-abs %.2e" % worst)
+    assert worst < 2e-4
