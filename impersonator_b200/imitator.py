@@ -517,6 +517,8 @@ class Imitator(object):
 
     def _last_frame_info(self):
         """tsf_info must describe the LAST frame (run_imitator.py:33-45 reads fim/T/tsf_img/cam/verts/wim)."""
+        if not self.tsf_info:                              # empty sequence: nothing was rendered
+            return
         info = dict(self.tsf_info)
         for k, v in list(info.items()):
             if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] >= 1:

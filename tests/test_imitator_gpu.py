@@ -232,6 +232,7 @@ def test_imitator_uint8_and_saved_frames(cuda, tmp_path):
         im.personalize("", src_smpl=src_theta, src_img=S.synthetic_source(size))
         tgt = np.zeros((3, 85), np.float32)
         tgt[:, 0], tgt[:, 3] = 0.9, np.array([0.2, 1.0, -2.0])
+        assert im.inference_by_smpls([]) == [] and im.inference([], tgt_smpls=[]) == []      # empty sequence (the reference returns [])
         floats = im.inference_by_smpls(list(tgt))
         u8 = im.inference_by_smpls(list(tgt), as_uint8=True)
         assert u8[0].dtype == np.uint8 and u8[0].shape == (size, size, 3)
