@@ -324,7 +324,7 @@ class Imitator(object):
         if not graphs_enabled() or B != bs or getattr(self._opt, 'front_warp', False):
             return self._chunk_pure(smpl, cam_strategy, hwc, u8)
         graphs = self.__dict__.setdefault('_graphs', {})
-        key = (B, cam_strategy, bool(hwc), bool(u8), id(self.src_info), os.environ.get("LWB_PRECISION"),
+        key = (B, int(smpl.shape[1]), cam_strategy, bool(hwc), bool(u8), id(self.src_info), os.environ.get("LWB_PRECISION"),
                os.environ.get("LWB_STREAMS"), self._ac, getattr(self.generator, '_lwb_precision', None), weights_epoch())
         step = graphs.get(key)
         if step is None:

@@ -168,5 +168,8 @@ def test_imitator_per_frame_api_host_logic_on_cpu(tmp_path, monkeypatch):
             worst = max(worst, float(np.abs(fr[1::4, 2::4] - g["imit_%s_%d" % (tag, t)]).max()))
         if tag == "smooth":
             assert np.abs(im.tsf_info["T"][:, 1::4, 2::4].numpy() - g["imit_last_T"]).max() < 1e-6
+            # demo_view.py:55-67 drives the Imitator with float64 [cam | pose] vectors of 75 entries (no shape part)
+            short = im.transfer_params_by_smpl(g["imit_thetas"][2][:75].astype(np.float64), strategy, t=2)
+            assert torch.equal(short, tsf_inputs)
     print("Imitator per-frame API on the kernel emulator vs the reference's frames: max-abs %.2e" % worst)
     assert worst < 2e-4
