@@ -471,6 +471,10 @@ class Imitator(object):
             drain(keep=1)
         drain(keep=0)
         self._last_frame_info()
+        if last_image[0] is None and length and tgt_paths[-1] and self.tsf_info:
+            # driven by given SMPL vectors AND frame files (evaluate.py:62): transfer_params still reads every frame file
+            # (models/imitator.py:270) and leaves the last one in tsf_info['image']; only that one is read here
+            _, last_image[0] = _read_image(tgt_paths[-1], self._opt.image_size)
         if last_image[0] is not None:
             self.tsf_info['image'] = last_image[0]
         if range_bits[0] and not getattr(self, '_range_retry', False):
