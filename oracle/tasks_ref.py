@@ -33,12 +33,14 @@ def morph(mask, ks, mode='erode'):                       # utils/util.py:73-89
     return (F.conv2d(F.pad(mask, [pad] * 4, value=0.0), kernel) >= 1).float()
 
 
-def personalize(img, cam, verts, faces, tabs, sd, size, task, part_fn=None, bg_ks=13, ft_ks=3):
+def personalize(img, cam, verts, faces, tabs, sd, size, task, part_fn=None, bg_ks=13, ft_ks=3, only_vis=False):
     """img [1,3,H,W] in [-1,1]; cam [1,3], verts [1,V,3] -> src_info.  ``task`` in {'imitator','viewer','swapper'} selects
     what is kept of the ORIGINAL background net's output (viewer.py:129 vs imitator.py:131 / swapper.py:148)."""
     f2v, fim, wim = nmr_ref.render_fim_wim(cam, verts, faces, size)
     cond = nmr_ref.encode_fim(fim, tabs["map_fn"])
     info = dict(cam=cam, verts=verts, fim=fim, wim=wim, cond=cond, f2verts=f2v, p2verts=nmr_ref.src_p2verts(f2v), img=img)
+    if only_vis:                                          # models/imitator.py:109-110: hidden faces' points -> -2
+        info['p2verts'] = nmr_ref.get_vis_f2pts(info['p2verts'], fim)
     if part_fn is not None:
         info['part'] = nmr_ref.encode_fim(fim, part_fn)
     bg_mask = morph(cond[:, -1:], bg_ks, 'erode')

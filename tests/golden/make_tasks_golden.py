@@ -113,7 +113,7 @@ def main():
         # ---- motion imitation: the reference Imitator itself (models/imitator.py:82-145, 192-268, 326-342) ----
         from models.imitator import Imitator
         for tag, opt, strategy in (("smooth", {}, "smooth"), ("front_source", dict(front_warp=True), "source"),
-                                   ("target", {}, "target")):
+                                   ("target", {}, "target"), ("only_vis", dict(only_vis=True), "smooth")):
             im = task(Imitator, **opt)
             im.src_info = im.tsf_info = im.first_cam = None
             im.personalize(a_png, src_smpl=SRC_THETA.copy())

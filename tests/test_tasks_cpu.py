@@ -8,6 +8,11 @@ from impersonator_b200 import synthetic as S
 from impersonator_b200.generator import ImpersonatorGenerator
 from oracle import tasks_ref as T
 
+# Network outputs: the restatement reproduces the reference's frames bit for bit in a quiet process (printed below), but
+# oneDNN's fp32 convolutions are not run-to-run deterministic under load (observed: 5e-5 on the background net), so the
+# gate is 2e-4 -- three orders of magnitude below what any orchestration error produces.  Flows / tables stay exact.
+NET_TOL = 2e-4
+
 
 def _setup(tmp_path):
     torch.set_grad_enabled(False)
@@ -24,14 +29,14 @@ def test_oracle_view_matches_reference_viewer(tmp_path):
     g, v, f, tabs, sd, a_png, _, body = _setup(tmp_path)
     d = body.get_details(torch.from_numpy(g["src_theta"])[None])
     info = T.personalize(C.read_like_reference(a_png), d["cam"], d["verts"], f, tabs, sd, C.SIZE, "viewer")
-    assert np.abs(C.sl(info["bg"]) - g["view_src_bg"]).max() < 1e-5
+    assert np.abs(C.sl(info["bg"]) - g["view_src_bg"]).max() < NET_TOL
     assert np.array_equal(C.sl(info["cond"]), g["view_src_cond"])
     for tag, kw in (("plain", {}), ("front_bg", dict(front_warp=True, bg_replace=True))):
         for i, (rt, t) in enumerate(g["views"]):
             preds, _ = T.view(info, rt / 180 * np.pi, t, f, tabs, sd, C.SIZE, **kw)
             err = np.abs(C.sl(preds) - g["view_%s_%d" % (tag, i)]).max()
             print("view %s %d: oracle vs reference max-abs %.2e" % (tag, i, err))
-            assert err < 1e-5
+            assert err < NET_TOL
 
 
 def test_oracle_swap_matches_reference_swapper(tmp_path):
@@ -43,13 +48,13 @@ def test_oracle_swap_matches_reference_swapper(tmp_path):
         infos.append(T.personalize(C.read_like_reference(png), d["cam"], d["verts"], f, tabs, sd, C.SIZE, "swapper", part_fn))
     src, tgt = infos
     assert np.array_equal(src["part"][:, :, 1::4, 2::4].numpy(), g["swap_src_part"])
-    assert np.abs(C.sl(tgt["bg"]) - g["swap_tgt_bg"]).max() < 1e-5
+    assert np.abs(C.sl(tgt["bg"]) - g["swap_tgt_bg"]).max() < NET_TOL
     for tag, fw in (("plain", False), ("front", True)):
         for part in ("body", "all"):
             preds, T11, T21 = T.swap(src, tgt, part_faces, tabs, sd, C.SIZE, part, front_warp=fw)
             err = np.abs(C.sl(preds) - g["swap_%s_%s" % (tag, part)]).max()
             print("swap %s %s: oracle vs reference max-abs %.2e" % (tag, part, err))
-            assert err < 1e-5
+            assert err < NET_TOL
             if tag == "plain" and part == "body":
                 assert np.array_equal(T11[:, 1::4, 2::4].numpy(), g["swap_T11"])
                 assert np.abs(T21[:, 1::4, 2::4].numpy() - g["swap_T21"]).max() < 1e-6
@@ -85,13 +90,16 @@ def test_oracle_imitation_matches_reference_imitator(tmp_path):
     g, v, f, tabs, sd, a_png, _, body = _setup(tmp_path)
     d = body.get_details(torch.from_numpy(g["src_theta"])[None])
     info = T.personalize(C.read_like_reference(a_png), d["cam"], d["verts"], f, tabs, sd, C.SIZE, "imitator")
-    assert np.abs(C.sl(info["bg"]) - g["imit_src_bg"]).max() < 1e-5
+    assert np.abs(C.sl(info["bg"]) - g["imit_src_bg"]).max() < NET_TOL
     thetas = torch.from_numpy(g["imit_thetas"])
-    for tag, strategy, fw in (("smooth", "smooth", False), ("front_source", "source", True), ("target", "target", False)):
-        outs, lastT = T.imitate(info, d["shape"], thetas, body, f, tabs, sd, C.SIZE, strategy, front_warp=fw)
+    vis = T.personalize(C.read_like_reference(a_png), d["cam"], d["verts"], f, tabs, sd, C.SIZE, "imitator", only_vis=True)
+    for tag, strategy, fw in (("smooth", "smooth", False), ("front_source", "source", True), ("target", "target", False),
+                              ("only_vis", "smooth", False)):
+        outs, lastT = T.imitate(vis if tag == "only_vis" else info, d["shape"], thetas, body, f, tabs, sd, C.SIZE, strategy,
+                                front_warp=fw)
         for t, fr in enumerate(outs):
             err = np.abs(fr[1::4, 2::4] - g["imit_%s_%d" % (tag, t)]).max()
-            assert err < 1e-5, (tag, t, err)
+            assert err < NET_TOL, (tag, t, err)
         if tag == "smooth":
             assert np.abs(lastT[:, 1::4, 2::4].numpy() - g["imit_last_T"]).max() < 1e-6
 
@@ -154,9 +162,10 @@ def test_imitator_per_frame_api_host_logic_on_cpu(tmp_path, monkeypatch):
     net = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6).eval()
     net.load_state_dict(sd)
     worst = 0.0
-    for tag, strategy, front in (("smooth", "smooth", False), ("front_source", "source", True), ("target", "target", False)):
+    for tag, strategy, front in (("smooth", "smooth", False), ("front_source", "source", True), ("target", "target", False),
+                                 ("only_vis", "smooth", False)):
         opt = C.Opt()
-        opt.front_warp = front
+        opt.front_warp, opt.only_vis = front, tag == "only_vis"
         render = SMPLRenderer(image_size=C.SIZE, faces=f.numpy(), map_fn=tabs["map_fn"], has_front=front,
                               front_map_fn=tabs["front_map_fn"], back_map_fn=tabs["back_map_fn"])
         im = Imitator(opt, generator=net, hmr=body, render=render, device="cpu")
