@@ -43,10 +43,15 @@ def conv_emul(fn, x, w, **kw):
     wh, wl = split(w)
     if MODE["name"] == "fp16x3":
         return fn(xh, wh, **kw) + fn(xh, wl, **kw) + fn(xl, wh, **kw)
+    if MODE["name"] == "fp16":
+        return fn(xh, wh, **kw)
     E = 14 - math.floor(math.log2(float(w.abs().max())))          # max|w| * 2^E in [2^14, 2^15)
-    t2 = fn(q8(x, 2.0 ** -4), q8(wl, 2.0 ** (E + 4)), **kw)
-    t3 = fn(q8(xl, 2.0 ** 10), q8(w, 2.0 ** (E - 10)), **kw)
-    return fn(xh, wh, **kw) + t2 + t3
+    out = fn(xh, wh, **kw)
+    if MODE["name"] != "fp16f8-no-wlo":
+        out = out + fn(q8(x, 2.0 ** -4), q8(wl, 2.0 ** (E + 4)), **kw)
+    if MODE["name"] != "fp16f8-no-xlo":
+        out = out + fn(q8(xl, 2.0 ** 10), q8(w, 2.0 ** (E - 10)), **kw)
+    return out
 
 
 _c2, _ct = F.conv2d, F.conv_transpose2d
@@ -99,5 +104,20 @@ def main():
                                                                      worst["fp16x3"][0], worst["fp16x3"][1]), flush=True)
 
 
+def variants():
+    """Why both correction products are needed: the benchmark weights with one of them dropped, and plain fp16."""
+    n = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    sd = S.fill_state_dict(n.state_dict(), seed=0)
+    size = int(os.environ.get("SIZE", "256"))
+    inp = S.synthetic_generator_inputs(1, size, seed=21)
+    MODE["name"] = "fp32"
+    a0, m0 = run(sd, inp)
+    for mode in ("fp16x3", "fp16f8", "fp16f8-no-xlo", "fp16f8-no-wlo", "fp16"):
+        MODE["name"] = mode
+        a, m = run(sd, inp)
+        print("%-14s colour %.2e  mask %.2e" % (mode, (torch.tanh(a) - torch.tanh(a0)).abs().max().item(),
+                                                (torch.sigmoid(m) - torch.sigmoid(m0)).abs().max().item()), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    variants() if "--variants" in sys.argv else main()
