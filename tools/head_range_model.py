@@ -43,7 +43,7 @@ def conv_emul(fn, x, w, **kw):
     wh, wl = split(w)
     if MODE["name"] == "fp16x3":
         return fn(xh, wh, **kw) + fn(xh, wl, **kw) + fn(xl, wh, **kw)
-    if MODE["name"] == "fp16":
+    if MODE["name"] == "fp16" or tuple(w.shape) in MODE.get("plain", ()):
         return fn(xh, wh, **kw)
     E = 14 - math.floor(math.log2(float(w.abs().max())))          # max|w| * 2^E in [2^14, 2^15)
     out = fn(xh, wh, **kw)
@@ -119,5 +119,31 @@ def variants():
                                                 (torch.sigmoid(m) - torch.sigmoid(m0)).abs().max().item()), flush=True)
 
 
+def per_layer():
+    """Which layers could run the single fp16 product (no correction MMAs) inside an otherwise fp16f8 network: the
+    layers are selected by weight shape (Conv2d [cout,cin,k,k]; ConvTranspose2d [cin,cout,k,k])."""
+    n = ImpersonatorGenerator(bg_dim=4, src_dim=6, tsf_dim=6, repeat_num=6)
+    sd = S.fill_state_dict(n.state_dict(), seed=0)
+    size = int(os.environ.get("SIZE", "256"))
+    inp = S.synthetic_generator_inputs(1, size, seed=21)
+    MODE["name"] = "fp32"
+    a0, m0 = run(sd, inp)
+    MODE["name"] = "fp16f8"
+    sets = [("none (fp16f8 everywhere)", ()),
+            ("heads 64->3/1 7x7", ((3, 64, 7, 7), (1, 64, 7, 7))),
+            ("stem 6->64 7x7", ((64, 6, 7, 7),)),
+            ("skipper 128->64 @256", ((64, 128, 3, 3),)),
+            ("convT 128->64", ((128, 64, 3, 3),)),
+            ("enc 64->128 s2", ((128, 64, 3, 3),)),
+            ("all of the above", ((3, 64, 7, 7), (1, 64, 7, 7), (64, 6, 7, 7), (64, 128, 3, 3), (128, 64, 3, 3))),
+            ("twelve 512->512", ((512, 512, 3, 3),))]
+    for name, shapes in sets:
+        MODE["plain"] = shapes
+        a, m = run(sd, inp)
+        print("%-28s colour %.2e  mask %.2e" % (name, (torch.tanh(a) - torch.tanh(a0)).abs().max().item(),
+                                                (torch.sigmoid(m) - torch.sigmoid(m0)).abs().max().item()), flush=True)
+    MODE.pop("plain", None)
+
+
 if __name__ == "__main__":
-    variants() if "--variants" in sys.argv else main()
+    per_layer() if "--per-layer" in sys.argv else variants() if "--variants" in sys.argv else main()
